@@ -1,0 +1,168 @@
+/*
+ * ugsm.h -- C-ABI of the B200-native ug_stereomatcher gpu_matcher hot path.
+ *
+ * This is the drop-in boundary.  Plain pointers and sizes only;
+ * no C++ / torch / OpenCV / ROS types.  Every entry point returns an int status
+ * (UGSM_OK == 0) and never throws or aborts across the boundary.
+ *
+ * What each entry point replaces in the reference (paths relative to the
+ * reference checkout, src/gpu_matcher/...):
+ *
+ *   ugsm_create / ugsm_destroy   MatchGPULib::MatchGPULib(argc, argv)   MatchGPULib.cpp:251-265
+ *                                (+ the per-pair cudaDeviceReset         MatchGPULib.cpp:400,528,696)
+ *   ugsm_match_full              MatchGPULib::match(L, R, fov=0)        MatchGPULib.cpp:303-403
+ *   ugsm_match_foveated          MatchGPULib::matchStackPyramid(...)    MatchGPULib.cpp:534-700
+ *                                MatchGPULib::matchStack(...)           MatchGPULib.cpp:429-531
+ *   ugsm_query_dims              MatchGPULib::initStack + getFovea*     MatchGPULib.cpp:268-278,406-426
+ *   ugsm_stage_*                 the 25 fine-grained extern "C" launch wrappers
+ *                                declared at MatchGPULib.cpp:45-247 / MatchLib_common.h:35-74
+ *                                (fused here; exposed per fused kernel for parity tests)
+ *
+ * Plane layout on the host side of this ABI: dense row-major float32, pitch == width,
+ * exactly what the reference hands to its ROS node (UG_GPU_matcher.cpp:430-471).
+ * RGB inputs: uint8 interleaved R,G,B with a row stride `step` in bytes
+ * (cv_bridge rgb8, MatchGPULib.cpp:332-338).
+ *
+ * Sign convention (getPointCloud.cpp:912-913): the pixel matching left (x, y) is
+ * right (x + H, y + V).
+ */
+#ifndef UGSM_H
+#define UGSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UGSM_MAX_LEVELS 14 /* MAX_LEVEL, MatchLib_common.h:13 */
+
+enum {
+    UGSM_OK = 0,
+    UGSM_ERR_INVALID = 1,  /* bad argument */
+    UGSM_ERR_CUDA = 2,     /* CUDA runtime error, see ugsm_last_error */
+    UGSM_ERR_NO_DEVICE = 3,
+    UGSM_ERR_NOMEM = 4
+};
+
+/* Iteration / pyramid schedule.  Defaults (ugsm_config_default) are the reference's
+ * compile-time constants and file globals. */
+typedef struct ugsm_config {
+    int32_t levels;             /* pyramid levels; MAX_LEVEL=14, MatchLib_common.h:13 */
+    int32_t fovea_level;        /* foveatelevel; argv[2], default 7, MatchGPULib.cpp:259-264 */
+    int32_t device;             /* CUDA device ordinal (-device=N, MatchGPULib.cpp:254); -1 = current */
+    int32_t iters_cutoff;       /* levelcutoff=22: iterations on levels i>5, MatchGPULib.cpp:37,1741 */
+    int32_t smooth_passes;      /* smoothtime=5, MatchGPULib.cpp:38 */
+    int32_t smooth_passes_fine; /* 10 on the two finest levels, MatchGPULib.cpp:2259-2261 */
+    int32_t max_iters;          /* 0 = reference schedule; >0 caps iterations per level (tests only) */
+    int32_t use_graph;          /* 1 = replay the level loop through CUDA graphs (default) */
+} ugsm_config;
+
+typedef struct ugsm_dims {
+    int32_t levels;
+    int32_t width[UGSM_MAX_LEVELS];  /* natural pyramid dims, w[i+1] = (int)(w[i]/1.41421356) */
+    int32_t height[UGSM_MAX_LEVELS];
+    int32_t match_width[UGSM_MAX_LEVELS];  /* dims the matcher runs at (fovea-cropped in foveated mode) */
+    int32_t match_height[UGSM_MAX_LEVELS];
+    int32_t iters[UGSM_MAX_LEVELS];         /* mi per level */
+    int32_t smooth[UGSM_MAX_LEVELS];        /* S per level */
+    int32_t fov_width, fov_height;          /* fovW, fovH (level fovea_level-1 dims) */
+    int32_t stack_rows;                     /* fovea_level * fov_height */
+    int64_t pixel_iterations;               /* sum over levels of match_w*match_h*mi */
+} ugsm_dims;
+
+/* Device-side timing of the last match call (CUDA events on the handle's stream). */
+typedef struct ugsm_timing {
+    float total_ms;      /* whole device-resident pair (pyramid .. final planes) */
+    float pyramid_ms;    /* unpack + pyramid of both images */
+    float levels_ms;     /* coarse-to-fine loop */
+    float h2d_ms, d2h_ms;
+    int32_t launches;    /* kernels launched by the last call */
+    float level_ms[UGSM_MAX_LEVELS];
+} ugsm_timing;
+
+typedef struct ugsm_handle ugsm_handle;
+
+void ugsm_config_default(ugsm_config* cfg);
+
+int ugsm_create(const ugsm_config* cfg, ugsm_handle** out);
+int ugsm_destroy(ugsm_handle* h);
+/* Last error text of this handle (never NULL).  With h == NULL: last creation error. */
+const char* ugsm_last_error(const ugsm_handle* h);
+
+/* Use an external CUDA stream (cudaStream_t passed as void*); NULL restores the handle's own. */
+int ugsm_set_stream(ugsm_handle* h, void* cuda_stream);
+
+/* mode: 0 = full pyramid, 1 = foveated.  Pure host arithmetic. */
+int ugsm_query_dims(const ugsm_config* cfg, int rows, int cols, int mode, ugsm_dims* out);
+
+/* Full-pyramid match.  Host buffers (pinned or pageable).  H, V, C: rows*cols floats each. */
+int ugsm_match_full(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step,
+                    float* H, float* V, float* C);
+
+/* Foveated match.  stackH/V/C: (fovea_level*fovH) x fovW floats, level-major rows
+ * (UG_GPU_matcher.cpp:293-303).  fovW/fovH may be NULL. */
+int ugsm_match_foveated(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step,
+                        float* stackH, float* stackV, float* stackC, int* fovW, int* fovH);
+
+/* Same two calls with every buffer already resident in device memory (the throughput
+ * path: no host<->device copies inside).  Output planes are dense (pitch == width). */
+int ugsm_match_full_device(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int rows, int cols,
+                           size_t step, float* dH, float* dV, float* dC);
+int ugsm_match_foveated_device(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int rows, int cols,
+                               size_t step, float* d_stackH, float* d_stackV, float* d_stackC);
+
+/* After a foveated match: copy the image foveas the reference exports through
+ * leftFov/rightFov (MatchGPULib.cpp:644-647) -- level `level`, 3 planes of
+ * match_width x match_height floats each, host buffers. */
+int ugsm_get_fovea_images(ugsm_handle* h, int level, float* left3, float* right3);
+
+/* After any match: copy pyramid level `level` of the left/right image (3 dense planes each). */
+int ugsm_get_pyramid_level(ugsm_handle* h, int level, float* left3, float* right3);
+/* After any match: copy the (H,V,C) state the matcher left on level `level`. */
+int ugsm_get_level_disparity(ugsm_handle* h, int level, float* H, float* V, float* C);
+
+int ugsm_get_timing(const ugsm_handle* h, ugsm_timing* out);
+
+/* ---- per-kernel stage entry points (host buffers; used by the parity tests and the
+ * roofline bench; they run exactly the kernels the match calls run) ---------------- */
+
+/* K0: RGB8 -> planar f32 + Gaussian pyramid.  out3[l] for l in [0,levels): 3 dense planes
+ * of width[l]*height[l]; entries may be NULL to skip the copy-out. */
+int ugsm_stage_pyramid(ugsm_handle* h, const uint8_t* rgb, int rows, int cols, size_t step, float* const* out3);
+
+/* K1: one fused warp + 5-offset NCC^2 + RGB mean + parabola fit + confidence blend.
+ * L3/R3: 3 dense planes each.  first_coarsest != 0 skips the confidence blend
+ * (MatchGPULib.cpp:2223).  Optional debug outputs (may be NULL): warp source indices
+ * and the PolyDisparity branch taken (0 flat, 1 concave, 2 concave-rescaled). */
+int ugsm_stage_correlate(ugsm_handle* h, const float* L3, const float* R3, const float* H, const float* V,
+                         const float* C, int width, int height, float threshold, int first_coarsest, float* Hn,
+                         float* Vn, float* Cn, int32_t* dbg_srcx, int32_t* dbg_srcy, uint8_t* dbg_branch_h,
+                         uint8_t* dbg_branch_v);
+
+/* K2: `passes` confidence-weighted cross smoothing passes followed by the 3x3 box filter, in place. */
+int ugsm_stage_smooth(ugsm_handle* h, float* H, float* V, float* C, int width, int height, int passes);
+
+/* K3: nearest-neighbour x sqrt(2) upsample of (H,V,C) to the next finer level; crop_x/crop_y/out_w/out_h
+ * select the centre crop of the foveated variant (MatchGPULib.cpp:1595-1655); for the plain variant
+ * pass crop 0,0 and out dims == fine dims. */
+int ugsm_stage_upsample(ugsm_handle* h, const float* H, const float* V, const float* C, int width, int height,
+                        int fine_w, int fine_h, int crop_x, int crop_y, int out_w, int out_h, float* Ho, float* Vo,
+                        float* Co);
+
+/* One whole level: `iters` iterations of K1+K2 with the reference threshold schedule. */
+int ugsm_stage_match_level(ugsm_handle* h, const float* L3, const float* R3, float* H, float* V, float* C, int width,
+                           int height, int iters, int passes, int coarsest);
+
+/* Micro-benchmark of K1 / K2 on device-resident synthetic planes: runs `reps` launches and
+ * returns the average per-launch time from CUDA events on the handle's stream. */
+int ugsm_bench_correlate(ugsm_handle* h, int width, int height, int reps, float* avg_ms);
+int ugsm_bench_smooth(ugsm_handle* h, int width, int height, int passes, int reps, float* avg_ms);
+
+const char* ugsm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UGSM_H */
