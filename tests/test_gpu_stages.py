@@ -1,0 +1,112 @@
+"""-m gpu: every fused kernel against the oracle on the same seeded inputs, bit-exact.
+
+All calls go through the C-ABI (ug_stereomatcher_b200/libugsm.so via ctypes).
+"""
+import numpy as np
+import pytest
+
+from ug_stereomatcher_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _state(rng, h, w, amp=2.0):
+    H = rng.uniform(-amp, amp, (h, w)).astype(np.float32)
+    V = rng.uniform(-amp / 2, amp / 2, (h, w)).astype(np.float32)
+    C = rng.uniform(0.2, 1.0, (h, w)).astype(np.float32)
+    return H, V, C
+
+
+def _planes(rgb):
+    return np.ascontiguousarray(rgb.transpose(2, 0, 1)).astype(np.float32)
+
+
+def _assert_same(a, b, what):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, what
+    same = (a == b) | (np.isnan(a) & np.isnan(b))
+    if not same.all():
+        bad = np.argwhere(~same)
+        i = tuple(bad[0])
+        raise AssertionError("%s: %d/%d differ, first at %s: gpu=%r oracle=%r, max|d|=%g" % (
+            what, len(bad), a.size, i, a[i], b[i], np.nanmax(np.abs(a.astype(np.float64) - b))))
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (407, 615), (34, 53), (4, 5), (61, 241), (16, 30), (17, 31)])
+def test_pyramid_bit_exact(gpu, oracle, capi, shape):
+    rows, cols = shape
+    levels = 14 if min(rows, cols) >= 400 else (6 if min(rows, cols) >= 30 else 2)
+    L, _, _, _ = synth.make_pair(cols, rows, 3)
+    with capi.Handle(levels=levels) as h:
+        got = h.stage_pyramid(L)
+    want = oracle.pyramid_rgb(L, levels)
+    for l in range(levels):
+        _assert_same(got[l], want[l], "pyramid level %d of %dx%d" % (l, cols, rows))
+
+
+@pytest.mark.parametrize("shape", [(118, 159), (34, 53), (4, 5), (16, 30), (17, 31), (33, 121), (100, 250)])
+@pytest.mark.parametrize("T,first", [(1.0, False), (0.46, False), (1.0, True)])
+def test_correlate_bit_exact(gpu, oracle, shape, T, first):
+    rows, cols = shape
+    rng = np.random.default_rng(rows * 1000 + cols)
+    L, R, _, _ = synth.make_pair(cols, rows, 1)
+    L3, R3 = _planes(L), _planes(R)
+    H, V, C = _state(rng, rows, cols)
+    got = gpu.stage_correlate(L3, R3, H, V, C, T, first, debug=True)
+    want = oracle.correlate(L3, R3, H, V, C, T, first, debug=True)
+    names = ["Hn", "Vn", "Cn", "srcx", "srcy", "branchH", "branchV"]
+    for g, w, n in zip(got, want, names):
+        _assert_same(g, w, "%s %dx%d T=%g first=%d" % (n, cols, rows, T, first))
+
+
+@pytest.mark.parametrize("shape", [(118, 159), (34, 53), (4, 5), (32, 64), (33, 65), (100, 250)])
+@pytest.mark.parametrize("passes", [0, 1, 5, 10])
+def test_smooth_bit_exact(gpu, oracle, shape, passes):
+    rows, cols = shape
+    rng = np.random.default_rng(7 + rows + cols + passes)
+    H, V, C = _state(rng, rows, cols)
+    got = gpu.stage_smooth(H, V, C, passes)
+    want = oracle.smooth(H, V, C, passes)
+    for g, w, n in zip(got, want, "HVC"):
+        _assert_same(g, w, "smooth %s %dx%d S=%d" % (n, cols, rows, passes))
+
+
+@pytest.mark.parametrize("src,fine", [((34, 53), (49, 75)), ((407, 615), (576, 870)), ((4, 5), (6, 8))])
+def test_upsample_bit_exact(gpu, oracle, src, fine):
+    rng = np.random.default_rng(11)
+    H, V, C = _state(rng, *src)
+    got = gpu.stage_upsample(H, V, C, fine[1], fine[0])
+    want = oracle.upsample_state(H, V, C, fine[1], fine[0])
+    for g, w, n in zip(got, want, "HVC"):
+        _assert_same(g, w, "upsample %s" % n)
+
+
+def test_upsample_crop_bit_exact(gpu, oracle):
+    """Foveated variant: 615x407 -> 870x576 then centre crop 615x407 at (128, 85) (MatchGPULib.cpp:1612-1615)."""
+    rng = np.random.default_rng(12)
+    H, V, C = _state(rng, 407, 615)
+    args = (870, 576, 870 // 2 - 615 // 2, 576 // 2 - 407 // 2, 615, 407)
+    assert args[2:4] == (128, 85)
+    got = gpu.stage_upsample(H, V, C, *args)
+    want = oracle.upsample_state(H, V, C, *args)
+    for g, w, n in zip(got, want, "HVC"):
+        _assert_same(g, w, "upsample+crop %s" % n)
+
+
+@pytest.mark.parametrize("shape,iters,passes,coarsest", [((58, 79), 22, 5, True), ((118, 159), 10, 5, False),
+                                                         ((83, 112), 4, 10, False)])
+def test_match_level_bit_exact(gpu, oracle, shape, iters, passes, coarsest):
+    rows, cols = shape
+    rng = np.random.default_rng(5)
+    L, R, _, _ = synth.make_pair(cols, rows, 2)
+    L3, R3 = _planes(L), _planes(R)
+    if coarsest:
+        H = np.zeros((rows, cols), np.float32)
+        V, C = H.copy(), H.copy()
+    else:
+        H, V, C = _state(rng, rows, cols, amp=1.0)
+    got = gpu.stage_match_level(L3, R3, H, V, C, iters, passes, coarsest)
+    want = oracle.match_level(L3, R3, H, V, C, iters, passes, coarsest)
+    for g, w, n in zip(got, want, "HVC"):
+        _assert_same(g, w, "match_level %s %dx%d" % (n, cols, rows))

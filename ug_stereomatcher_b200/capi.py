@@ -1,0 +1,297 @@
+"""ctypes binding of the C-ABI in include/ugsm.h (ug_stereomatcher_b200/libugsm.so).
+
+There is no CPU fallback: if the library is missing or no sm_100 device is present the
+calls raise.  Nothing here imports the oracle.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libugsm.so")
+MAX_LEVELS = 14
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM = 0, 1, 2, 3, 4
+
+# Every symbol include/ugsm.h declares (checked by tests/test_abi.py against the header).
+SYMBOLS = [
+    "ugsm_config_default", "ugsm_create", "ugsm_destroy", "ugsm_last_error", "ugsm_set_stream", "ugsm_query_dims",
+    "ugsm_match_full", "ugsm_match_foveated", "ugsm_match_full_device", "ugsm_match_foveated_device",
+    "ugsm_get_fovea_images", "ugsm_get_pyramid_level", "ugsm_get_level_disparity", "ugsm_get_timing",
+    "ugsm_stage_pyramid", "ugsm_stage_correlate", "ugsm_stage_smooth", "ugsm_stage_upsample",
+    "ugsm_stage_match_level", "ugsm_bench_correlate", "ugsm_bench_smooth", "ugsm_version",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("levels", C.c_int32),
+        ("fovea_level", C.c_int32),
+        ("device", C.c_int32),
+        ("iters_cutoff", C.c_int32),
+        ("smooth_passes", C.c_int32),
+        ("smooth_passes_fine", C.c_int32),
+        ("max_iters", C.c_int32),
+        ("use_graph", C.c_int32),
+    ]
+
+
+class Dims(C.Structure):
+    _fields_ = [
+        ("levels", C.c_int32),
+        ("width", C.c_int32 * MAX_LEVELS),
+        ("height", C.c_int32 * MAX_LEVELS),
+        ("match_width", C.c_int32 * MAX_LEVELS),
+        ("match_height", C.c_int32 * MAX_LEVELS),
+        ("iters", C.c_int32 * MAX_LEVELS),
+        ("smooth", C.c_int32 * MAX_LEVELS),
+        ("fov_width", C.c_int32),
+        ("fov_height", C.c_int32),
+        ("stack_rows", C.c_int32),
+        ("pixel_iterations", C.c_int64),
+    ]
+
+
+class Timing(C.Structure):
+    _fields_ = [
+        ("total_ms", C.c_float),
+        ("pyramid_ms", C.c_float),
+        ("levels_ms", C.c_float),
+        ("h2d_ms", C.c_float),
+        ("d2h_ms", C.c_float),
+        ("launches", C.c_int32),
+        ("level_ms", C.c_float * MAX_LEVELS),
+    ]
+
+
+class UgsmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("ugsm error %d: %s" % (code, msg))
+        self.code = code
+
+
+_LIB = None
+
+
+def build():
+    """Compile libugsm.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(_HERE, "csrc")], check=True)
+
+
+def lib():
+    """Load libugsm.so.  Raises if it has not been built -- there is no fallback."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise UgsmError(-1, "libugsm.so not built (run __graft_entry__.build() or make -C "
+                                "ug_stereomatcher_b200/csrc); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.ugsm_last_error.restype = C.c_char_p
+        L.ugsm_last_error.argtypes = [C.c_void_p]
+        L.ugsm_version.restype = C.c_char_p
+        L.ugsm_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        L.ugsm_destroy.argtypes = [C.c_void_p]
+        L.ugsm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.ugsm_query_dims.argtypes = [C.POINTER(Config), C.c_int, C.c_int, C.c_int, C.POINTER(Dims)]
+        vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+        L.ugsm_match_full.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp]
+        L.ugsm_match_foveated.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp, C.POINTER(i), C.POINTER(i)]
+        L.ugsm_match_full_device.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp]
+        L.ugsm_match_foveated_device.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp]
+        L.ugsm_get_fovea_images.argtypes = [vp, i, vp, vp]
+        L.ugsm_get_pyramid_level.argtypes = [vp, i, vp, vp]
+        L.ugsm_get_level_disparity.argtypes = [vp, i, vp, vp, vp]
+        L.ugsm_get_timing.argtypes = [vp, C.POINTER(Timing)]
+        L.ugsm_stage_pyramid.argtypes = [vp, vp, i, i, sz, C.POINTER(vp)]
+        L.ugsm_stage_correlate.argtypes = [vp, vp, vp, vp, vp, vp, i, i, C.c_float, i, vp, vp, vp, vp, vp, vp, vp]
+        L.ugsm_stage_smooth.argtypes = [vp, vp, vp, vp, i, i, i]
+        L.ugsm_stage_upsample.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp]
+        L.ugsm_stage_match_level.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i]
+        L.ugsm_bench_correlate.argtypes = [vp, i, i, i, C.POINTER(C.c_float)]
+        L.ugsm_bench_smooth.argtypes = [vp, i, i, i, i, C.POINTER(C.c_float)]
+        _LIB = L
+    return _LIB
+
+
+def default_config(**kw):
+    cfg = Config()
+    lib().ugsm_config_default(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def query_dims(cfg, rows, cols, mode=0):
+    d = Dims()
+    rc = lib().ugsm_query_dims(C.byref(cfg), rows, cols, mode, C.byref(d))
+    if rc != OK:
+        raise UgsmError(rc, "ugsm_query_dims: invalid rows/cols/mode/config")
+    return d
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Handle:
+    """One matcher instance: one CUDA stream, its own device buffers, not thread-safe."""
+
+    def __init__(self, cfg=None, **kw):
+        self.cfg = cfg if cfg is not None else default_config(**kw)
+        self._h = C.c_void_p()
+        rc = lib().ugsm_create(C.byref(self.cfg), C.byref(self._h))
+        if rc != OK:
+            raise UgsmError(rc, lib().ugsm_last_error(None).decode())
+
+    def close(self):
+        if self._h:
+            lib().ugsm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise UgsmError(rc, lib().ugsm_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(lib().ugsm_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def timing(self):
+        t = Timing()
+        self._ck(lib().ugsm_get_timing(self._h, C.byref(t)))
+        return t
+
+    # -- whole-pair calls, host buffers ------------------------------------------------
+    def match_full(self, rgbL, rgbR, out=None):
+        rgbL = np.ascontiguousarray(rgbL, np.uint8)
+        rgbR = np.ascontiguousarray(rgbR, np.uint8)
+        rows, cols, ch = rgbL.shape
+        if ch != 3 or rgbR.shape != rgbL.shape:
+            raise UgsmError(ERR_INVALID, "expected two (rows, cols, 3) uint8 images of equal shape")
+        if out is None:
+            out = tuple(np.empty((rows, cols), np.float32) for _ in range(3))
+        H, V, Cc = out
+        self._ck(lib().ugsm_match_full(self._h, _p(rgbL), _p(rgbR), rows, cols, rgbL.strides[0], _p(H), _p(V), _p(Cc)))
+        return H, V, Cc
+
+    def match_foveated(self, rgbL, rgbR):
+        rgbL = np.ascontiguousarray(rgbL, np.uint8)
+        rgbR = np.ascontiguousarray(rgbR, np.uint8)
+        rows, cols, ch = rgbL.shape
+        if ch != 3 or rgbR.shape != rgbL.shape:
+            raise UgsmError(ERR_INVALID, "expected two (rows, cols, 3) uint8 images of equal shape")
+        d = query_dims(self.cfg, rows, cols, 1)
+        shape = (d.stack_rows, d.fov_width)
+        sH, sV, sC = (np.empty(shape, np.float32) for _ in range(3))
+        fw, fh = C.c_int(), C.c_int()
+        self._ck(lib().ugsm_match_foveated(self._h, _p(rgbL), _p(rgbR), rows, cols, rgbL.strides[0], _p(sH), _p(sV),
+                                           _p(sC), C.byref(fw), C.byref(fh)))
+        return sH, sV, sC, fw.value, fh.value
+
+    # -- whole-pair calls, device pointers (ints) ----------------------------------------
+    def match_full_device(self, d_rgbL, d_rgbR, rows, cols, step, dH, dV, dC):
+        self._ck(lib().ugsm_match_full_device(self._h, d_rgbL, d_rgbR, rows, cols, step, dH, dV, dC))
+
+    def match_foveated_device(self, d_rgbL, d_rgbR, rows, cols, step, dH, dV, dC):
+        self._ck(lib().ugsm_match_foveated_device(self._h, d_rgbL, d_rgbR, rows, cols, step, dH, dV, dC))
+
+    # -- inspection after a match ---------------------------------------------------------
+    def pyramid_level(self, level, rows, cols, mode=0):
+        d = query_dims(self.cfg, rows, cols, mode)
+        shape = (3, d.height[level], d.width[level])
+        L, R = np.empty(shape, np.float32), np.empty(shape, np.float32)
+        self._ck(lib().ugsm_get_pyramid_level(self._h, level, _p(L), _p(R)))
+        return L, R
+
+    def fovea_images(self, level, rows, cols, mode=1):
+        d = query_dims(self.cfg, rows, cols, mode)
+        shape = (3, d.match_height[level], d.match_width[level])
+        L, R = np.empty(shape, np.float32), np.empty(shape, np.float32)
+        self._ck(lib().ugsm_get_fovea_images(self._h, level, _p(L), _p(R)))
+        return L, R
+
+    def level_disparity(self, level, rows, cols, mode=0):
+        d = query_dims(self.cfg, rows, cols, mode)
+        shape = (d.match_height[level], d.match_width[level])
+        H, V, Cc = (np.empty(shape, np.float32) for _ in range(3))
+        self._ck(lib().ugsm_get_level_disparity(self._h, level, _p(H), _p(V), _p(Cc)))
+        return H, V, Cc
+
+    # -- per-kernel stages ------------------------------------------------------------------
+    def stage_pyramid(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        rows, cols, _ = rgb.shape
+        d = query_dims(self.cfg, rows, cols, 0)
+        outs = [np.empty((3, d.height[l], d.width[l]), np.float32) for l in range(d.levels)]
+        arr = (C.c_void_p * d.levels)(*[o.ctypes.data for o in outs])
+        self._ck(lib().ugsm_stage_pyramid(self._h, _p(rgb), rows, cols, rgb.strides[0], arr))
+        return outs
+
+    def stage_correlate(self, L3, R3, H, V, Cc, T, first_coarsest=False, debug=False):
+        L3, R3, H, V, Cc = map(_f32, (L3, R3, H, V, Cc))
+        _, h, w = L3.shape
+        Hn, Vn, Cn = np.empty_like(H), np.empty_like(V), np.empty_like(Cc)
+        if debug:
+            sx, sy = np.empty((h, w), np.int32), np.empty((h, w), np.int32)
+            bh, bv = np.empty((h, w), np.uint8), np.empty((h, w), np.uint8)
+        else:
+            sx = sy = bh = bv = None
+        self._ck(lib().ugsm_stage_correlate(self._h, _p(L3), _p(R3), _p(H), _p(V), _p(Cc), w, h, T,
+                                            int(first_coarsest), _p(Hn), _p(Vn), _p(Cn), _p(sx), _p(sy), _p(bh),
+                                            _p(bv)))
+        if debug:
+            return Hn, Vn, Cn, sx, sy, bh, bv
+        return Hn, Vn, Cn
+
+    def stage_smooth(self, H, V, Cc, passes):
+        H, V, Cc = _f32(H).copy(), _f32(V).copy(), _f32(Cc).copy()
+        h, w = H.shape
+        self._ck(lib().ugsm_stage_smooth(self._h, _p(H), _p(V), _p(Cc), w, h, passes))
+        return H, V, Cc
+
+    def stage_upsample(self, H, V, Cc, fine_w, fine_h, crop_x=0, crop_y=0, out_w=None, out_h=None):
+        H, V, Cc = map(_f32, (H, V, Cc))
+        h, w = H.shape
+        out_w = fine_w if out_w is None else out_w
+        out_h = fine_h if out_h is None else out_h
+        outs = [np.empty((out_h, out_w), np.float32) for _ in range(3)]
+        self._ck(lib().ugsm_stage_upsample(self._h, _p(H), _p(V), _p(Cc), w, h, fine_w, fine_h, crop_x, crop_y, out_w,
+                                           out_h, *[_p(o) for o in outs]))
+        return tuple(outs)
+
+    def stage_match_level(self, L3, R3, H, V, Cc, iters, passes, coarsest):
+        L3, R3 = _f32(L3), _f32(R3)
+        H, V, Cc = _f32(H).copy(), _f32(V).copy(), _f32(Cc).copy()
+        _, h, w = L3.shape
+        self._ck(lib().ugsm_stage_match_level(self._h, _p(L3), _p(R3), _p(H), _p(V), _p(Cc), w, h, iters, passes,
+                                              int(coarsest)))
+        return H, V, Cc
+
+    def bench_correlate(self, width, height, reps=10):
+        ms = C.c_float()
+        self._ck(lib().ugsm_bench_correlate(self._h, width, height, reps, C.byref(ms)))
+        return ms.value
+
+    def bench_smooth(self, width, height, passes, reps=10):
+        ms = C.c_float()
+        self._ck(lib().ugsm_bench_smooth(self._h, width, height, passes, reps, C.byref(ms)))
+        return ms.value

@@ -1,0 +1,1030 @@
+// ugsm.cu -- host-side level driver and the C-ABI (include/ugsm.h) over the sm_100a kernels.
+//
+// Mirrors the orchestration of the reference's MatchGPULib (src/gpu_matcher/MatchGPULib.cpp):
+//   match()               MGL:303-403    -> ugsm_match_full
+//   matchStackPyramid()   MGL:534-700    -> ugsm_match_foveated
+//   CreatePyramidFromImage MGL:1033-1125 -> build_pyramid()
+//   CreateFoveatedPyramid MGL:1128-1190  -> crops in prepare_levels()
+//   matching()            MGL:1196-1318  -> run_levels()
+//   matchlevel()          MGL:1662-2489  -> run_level()  (K1 + K2 per iteration)
+//   subsampleDisp / foveatedsubsampleDisp MGL:1526-1655 -> K3
+// but keeps everything resident on the device: no host round trips inside a pair, one
+// stream per handle, no global device state, no cudaDeviceReset.
+#include "../../include/ugsm.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ugsm_kernels.cuh"
+
+using namespace ugsm;
+
+#define SCALE_D 1.41421356 /* MatchLib_common.h:15 */
+
+namespace {
+
+std::string g_create_error;
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+struct LevelBuf {
+    int w = 0, h = 0, pitch = 0;     // natural pyramid dims
+    int mw = 0, mh = 0, mpitch = 0;  // dims the matcher runs at
+    int crop_x = 0, crop_y = 0;
+    bool cropped = false;
+    float* L[3] = {nullptr, nullptr, nullptr};
+    float* R[3] = {nullptr, nullptr, nullptr};
+    float* Lm[3] = {nullptr, nullptr, nullptr};  // == L/R unless cropped
+    float* Rm[3] = {nullptr, nullptr, nullptr};
+    float* U[3] = {nullptr, nullptr, nullptr};
+    float* st[3] = {nullptr, nullptr, nullptr};  // H, V, C
+    int iters = 0, smooth = 0;
+};
+
+}  // namespace
+
+struct ugsm_handle {
+    ugsm_config cfg;
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    Taps taps;
+    int sm_count = 148;
+
+    // shape-dependent state
+    int rows = 0, cols = 0, mode = -1;
+    ugsm_dims dims;
+    std::vector<LevelBuf> lv;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    float* tmp[3] = {nullptr, nullptr, nullptr};  // K1 output / K2 input
+    uint8_t* d_rgb[2] = {nullptr, nullptr};       // staging for the host-buffer entry points
+    size_t d_rgb_bytes = 0;
+    float* d_out[3] = {nullptr, nullptr, nullptr};  // dense output staging
+    size_t d_out_floats = 0;
+
+    cudaEvent_t ev[4 + UGSM_MAX_LEVELS] = {};
+    ugsm_timing timing;
+    int launches = 0;
+    bool k_attr_set = false;
+};
+
+namespace {
+
+int fail(ugsm_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h)
+        h->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(h, UGSM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                           \
+    } while (0)
+
+// MGL:761-775 and MGL:344-348, evaluated in float exactly as the host code does.
+void make_taps(Taps& t) {
+    float k[5];
+    k[0] = 0.0816475;
+    k[1] = 0.218507;
+    k[2] = 0.303281;
+    k[3] = 0.218507;
+    k[4] = 0.0816475;
+    float kern = 0;
+    for (int i = 0; i < 5; i++) kern = kern + k[i];
+    for (int i = 0; i < 5; i++) t.g[i] = k[i] / kern;
+    t.a[0] = 0.0;
+    t.a[1] = 0.3333;
+    t.a[2] = 0.3333;
+    t.a[3] = 0.3333;
+    t.a[4] = 0.0;
+}
+
+int level_iters(const ugsm_config& c, int i) {  // MGL:1741 with level = MAX_LEVEL-1-i
+    int mi = (i > 5) ? c.iters_cutoff : ((i + 1) * 2);
+    if (c.max_iters > 0 && mi > c.max_iters) mi = c.max_iters;
+    return mi;
+}
+int level_smooth(const ugsm_config& c, int i) {  // MGL:2257-2261
+    return (i < 2) ? c.smooth_passes_fine : c.smooth_passes;
+}
+// MGL:2299-2306: evaluated after iteration m, applies from iteration m+1.
+float threshold_after(int mi, int m, float T) {
+    float threshold = T;
+    if (m % 2 == 0) {
+        if ((mi / 2 - m / 2) < 7) {
+            threshold = ((mi / 2 - m / 2) - 1) * ((1 - 0.1) / (mi / 2 - 1.0)) + 0.1;
+        } else {
+            threshold = 1.0;
+        }
+    }
+    return threshold;
+}
+
+int validate_cfg(const ugsm_config& c) {
+    if (c.levels < 1 || c.levels > UGSM_MAX_LEVELS) return 0;
+    if (c.iters_cutoff < 1 || c.smooth_passes < 0 || c.smooth_passes_fine < 0) return 0;
+    if (c.smooth_passes > 16 || c.smooth_passes_fine > 16) return 0;
+    return 1;
+}
+
+int compute_dims(const ugsm_config& c, int rows, int cols, int mode, ugsm_dims* d) {
+    if (!validate_cfg(c) || rows < 1 || cols < 1 || (mode != 0 && mode != 1)) return UGSM_ERR_INVALID;
+    memset(d, 0, sizeof *d);
+    d->levels = c.levels;
+    d->width[0] = cols;
+    d->height[0] = rows;
+    for (int i = 0; i + 1 < c.levels; i++) {  // MGL:1224-1228
+        d->width[i + 1] = d->width[i] / SCALE_D;
+        d->height[i + 1] = d->height[i] / SCALE_D;
+    }
+    if (d->width[c.levels - 1] < 1 || d->height[c.levels - 1] < 1) return UGSM_ERR_INVALID;
+    int fl = c.fovea_level;
+    if (mode == 1 && (fl < 2 || fl > c.levels)) return UGSM_ERR_INVALID;
+    if (fl >= 1 && fl <= c.levels) {
+        d->fov_width = d->width[fl - 1];
+        d->fov_height = d->height[fl - 1];
+        d->stack_rows = fl * d->fov_height;
+    }
+    for (int i = 0; i < c.levels; i++) {
+        bool crop = (mode == 1 && i < fl - 1);  // MGL:1230-1240
+        d->match_width[i] = crop ? d->fov_width : d->width[i];
+        d->match_height[i] = crop ? d->fov_height : d->height[i];
+        d->iters[i] = level_iters(c, i);
+        d->smooth[i] = level_smooth(c, i);
+        d->pixel_iterations += (int64_t)d->match_width[i] * d->match_height[i] * d->iters[i];
+    }
+    return UGSM_OK;
+}
+
+// ------------------------------------------------------------------ kernel launchers
+constexpr int K1_TH = 16;
+constexpr int K2_TW = 64, K2_TH = 32;
+
+size_t k2_smem_bytes(int passes) {
+    int R = passes + 1;
+    return (size_t)2 * 3 * (K2_TW + 2 * R) * (K2_TH + 2 * R) * sizeof(float);
+}
+
+int set_kernel_attrs(ugsm_handle* h) {
+    if (h->k_attr_set) return UGSM_OK;
+    CK(cudaFuncSetAttribute(k1_correlate<4, K1_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(K1Smem<4, K1_TH>)));
+    CK(cudaFuncSetAttribute(k1_correlate<1, K1_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(K1Smem<1, K1_TH>)));
+    CK(cudaFuncSetAttribute(k2_smooth_box<K2_TW, K2_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)k2_smem_bytes(16)));
+    h->k_attr_set = true;
+    return UGSM_OK;
+}
+
+void launch_k1(ugsm_handle* h, const K1Params& p) {
+    // Wide levels: 4-warp CTAs (120 columns); narrow ones: 1-warp CTAs so that the few
+    // tiles there are spread over more SMs.
+    long tiles4 = (long)div_up(p.w, 120) * div_up(p.h, K1_TH);
+    if (tiles4 >= 2L * h->sm_count) {
+        dim3 grid(div_up(p.w, 120), div_up(p.h, K1_TH));
+        k1_correlate<4, K1_TH><<<grid, 128, sizeof(K1Smem<4, K1_TH>), h->stream>>>(p);
+    } else {
+        dim3 grid(div_up(p.w, 30), div_up(p.h, K1_TH));
+        k1_correlate<1, K1_TH><<<grid, 32, sizeof(K1Smem<1, K1_TH>), h->stream>>>(p);
+    }
+    h->launches++;
+}
+
+void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci, float* Ho, float* Vo, float* Co,
+               int w, int hh, int pitch, int passes) {
+    K2Params p;
+    p.Hi = Hi;
+    p.Vi = Vi;
+    p.Ci = Ci;
+    p.Ho = Ho;
+    p.Vo = Vo;
+    p.Co = Co;
+    p.w = w;
+    p.h = hh;
+    p.pitch = pitch;
+    p.passes = passes;
+    p.a1 = h->taps.a[1];
+    dim3 grid(div_up(w, K2_TW), div_up(hh, K2_TH));
+    k2_smooth_box<K2_TW, K2_TH><<<grid, 256, k2_smem_bytes(passes), h->stream>>>(p);
+    h->launches++;
+}
+
+void launch_k3(ugsm_handle* h, float* const src[3], int w, int hh, int spitch, int crop_x, int crop_y,
+               float* const dst[3], int ow, int oh, int dpitch) {
+    dim3 block(32, 8), grid(div_up(ow, 32), div_up(oh, 8));
+    k3_upsample<<<grid, block, 0, h->stream>>>(src[0], src[1], src[2], w, hh, spitch, crop_x, crop_y, dst[0], dst[1],
+                                               dst[2], ow, oh, dpitch);
+    h->launches++;
+}
+
+void launch_energy(ugsm_handle* h, const float* L, int w, int hh, int pitch, float* U) {
+    dim3 block(32, 8), grid(div_up(w, 32), div_up(hh, 8));
+    k0_left_energy<<<grid, block, 0, h->stream>>>(L, w, hh, pitch, U, h->taps);
+    h->launches++;
+}
+
+void launch_unpack(ugsm_handle* h, const uint8_t* rgb, size_t step, int w, int hh, float* const pl[3], int pitch) {
+    dim3 grid(div_up(w, 256), hh);
+    k0_unpack_rgb8<<<grid, 256, 0, h->stream>>>(rgb, step, w, hh, pl[0], pl[1], pl[2], pitch);
+    h->launches++;
+}
+
+void launch_blur_decimate(ugsm_handle* h, int mode, const float* src, int w, int hh, int spitch, float* dst, int w2,
+                          int h2, int dpitch) {
+    dim3 block(32, 8), grid(div_up(w2, 32), div_up(h2, 8));
+    if (mode == 0) {
+        float s = SCALE_D;  // MGL:1083
+        k0_blur_decimate<0><<<grid, block, 0, h->stream>>>(src, w, hh, spitch, dst, w2, h2, dpitch, s, h->taps);
+    } else {
+        float s = 0.000 + (int)(SCALE_D * SCALE_D + 0.5);  // MGL:1090
+        k0_blur_decimate<1><<<grid, block, 0, h->stream>>>(src, w, hh, spitch, dst, w2, h2, dpitch, s, h->taps);
+    }
+    h->launches++;
+}
+
+void launch_copy3(ugsm_handle* h, const float* s0, const float* s1, const float* s2, int spitch, float* d0, float* d1,
+                  float* d2, int dpitch, int w, int hh) {
+    dim3 grid(div_up(w, 256), hh);
+    k_copy3<<<grid, 256, 0, h->stream>>>(s0, s1, s2, spitch, d0, d1, d2, dpitch, w, hh);
+    h->launches++;
+}
+
+// ------------------------------------------------------------------ per-shape buffers
+void release_shape(ugsm_handle* h) {
+    if (h->arena) cudaFree(h->arena);
+    h->arena = nullptr;
+    h->arena_bytes = 0;
+    h->lv.clear();
+    h->rows = h->cols = 0;
+    h->mode = -1;
+}
+
+int prepare_shape(ugsm_handle* h, int rows, int cols, int mode) {
+    if (h->arena && h->rows == rows && h->cols == cols && h->mode == mode) return UGSM_OK;
+    release_shape(h);
+    ugsm_dims d;
+    int rc = compute_dims(h->cfg, rows, cols, mode, &d);
+    if (rc != UGSM_OK) return fail(h, rc, "invalid shape/config: rows=%d cols=%d mode=%d levels=%d", rows, cols, mode,
+                                   h->cfg.levels);
+    const int levels = h->cfg.levels;
+    std::vector<LevelBuf> lv(levels);
+    size_t total = 0;
+    auto plane_bytes = [](int pitch, int hh) { return ((size_t)pitch * hh * sizeof(float) + 255) / 256 * 256; };
+    size_t max_match = 0;
+    for (int i = 0; i < levels; i++) {
+        LevelBuf& b = lv[i];
+        b.w = d.width[i];
+        b.h = d.height[i];
+        b.pitch = align_up(b.w, 32);
+        b.mw = d.match_width[i];
+        b.mh = d.match_height[i];
+        b.mpitch = align_up(b.mw, 32);
+        b.cropped = (b.mw != b.w || b.mh != b.h);
+        if (b.cropped) {  // MGL:1143-1176: l = x/2 - fovW/2, u = y/2 - fovH/2
+            b.crop_x = b.w / 2 - b.mw / 2;
+            b.crop_y = b.h / 2 - b.mh / 2;
+        }
+        b.iters = d.iters[i];
+        b.smooth = d.smooth[i];
+        total += 6 * plane_bytes(b.pitch, b.h);
+        if (b.cropped) total += 6 * plane_bytes(b.mpitch, b.mh);
+        total += 6 * plane_bytes(b.mpitch, b.mh);  // U[3] + state[3]
+        size_t mb = plane_bytes(b.mpitch, b.mh);
+        if (mb > max_match) max_match = mb;
+    }
+    total += 3 * max_match;
+    CK(cudaMalloc(&h->arena, total));
+    h->arena_bytes = total;
+    char* cur = static_cast<char*>(h->arena);
+    auto take = [&](size_t bytes) {
+        float* p = reinterpret_cast<float*>(cur);
+        cur += bytes;
+        return p;
+    };
+    for (int i = 0; i < levels; i++) {
+        LevelBuf& b = lv[i];
+        for (int k = 0; k < 3; k++) b.L[k] = take(plane_bytes(b.pitch, b.h));
+        for (int k = 0; k < 3; k++) b.R[k] = take(plane_bytes(b.pitch, b.h));
+        for (int k = 0; k < 3; k++) {
+            b.Lm[k] = b.cropped ? take(plane_bytes(b.mpitch, b.mh)) : b.L[k];
+            b.Rm[k] = b.cropped ? take(plane_bytes(b.mpitch, b.mh)) : b.R[k];
+        }
+        for (int k = 0; k < 3; k++) b.U[k] = take(plane_bytes(b.mpitch, b.mh));
+        for (int k = 0; k < 3; k++) b.st[k] = take(plane_bytes(b.mpitch, b.mh));
+    }
+    for (int k = 0; k < 3; k++) h->tmp[k] = take(max_match);
+    h->lv.swap(lv);
+    h->dims = d;
+    h->rows = rows;
+    h->cols = cols;
+    h->mode = mode;
+    return UGSM_OK;
+}
+
+// MGL:1033-1125 for one image (three channels).
+void build_pyramid(ugsm_handle* h, const uint8_t* d_rgb, size_t step, bool right) {
+    const int levels = h->cfg.levels;
+    auto planes = [&](int i) { return right ? h->lv[i].R : h->lv[i].L; };
+    launch_unpack(h, d_rgb, step, h->lv[0].w, h->lv[0].h, planes(0), h->lv[0].pitch);
+    for (int i = 0; i < levels; i++) {
+        const LevelBuf& s = h->lv[i];
+        for (int k = 0; k < 3; k++) {
+            if (i == 0 && levels > 1)
+                launch_blur_decimate(h, 0, planes(0)[k], s.w, s.h, s.pitch, planes(1)[k], h->lv[1].w, h->lv[1].h,
+                                     h->lv[1].pitch);
+            if (i + 2 < levels)
+                launch_blur_decimate(h, 1, planes(i)[k], s.w, s.h, s.pitch, planes(i + 2)[k], h->lv[i + 2].w,
+                                     h->lv[i + 2].h, h->lv[i + 2].pitch);
+        }
+    }
+}
+
+// Foveated crops (MGL:1171-1185) and the per-level left-image energy U.
+void prepare_levels(ugsm_handle* h) {
+    for (auto& b : h->lv) {
+        if (b.cropped) {
+            dim3 grid(div_up(b.mw, 256), b.mh);
+            for (int k = 0; k < 3; k++) {
+                k_crop<<<grid, 256, 0, h->stream>>>(b.L[k], b.pitch, b.crop_x, b.crop_y, b.Lm[k], b.mw, b.mh,
+                                                    b.mpitch);
+                k_crop<<<grid, 256, 0, h->stream>>>(b.R[k], b.pitch, b.crop_x, b.crop_y, b.Rm[k], b.mw, b.mh,
+                                                    b.mpitch);
+                h->launches += 2;
+            }
+        }
+        for (int k = 0; k < 3; k++) launch_energy(h, b.Lm[k], b.mw, b.mh, b.mpitch, b.U[k]);
+    }
+}
+
+// MGL:1662-2489: `iters` iterations of K1 (correlate/fit/blend) + K2 (smooth/box).
+void run_level(ugsm_handle* h, float* const L[3], float* const R[3], float* const U[3], float* const st[3],
+               float* const tmp[3], int w, int hh, int pitch, int iters, int passes, bool coarsest) {
+    float T = 1.0f;  // MGL:1673
+    for (int m = 1; m <= iters; m++) {
+        K1Params p;
+        for (int k = 0; k < 3; k++) {
+            p.L[k] = L[k];
+            p.R[k] = R[k];
+            p.U[k] = U[k];
+        }
+        p.H = st[0];
+        p.V = st[1];
+        p.C = st[2];
+        p.Hn = tmp[0];
+        p.Vn = tmp[1];
+        p.Cn = tmp[2];
+        p.w = w;
+        p.h = hh;
+        p.pitch = pitch;
+        p.T = T;
+        p.first_coarsest = (coarsest && m == 1) ? 1 : 0;
+        p.dbg_srcx = nullptr;
+        p.dbg_srcy = nullptr;
+        p.dbg_bh = nullptr;
+        p.dbg_bv = nullptr;
+        p.tp = h->taps;
+        launch_k1(h, p);
+        launch_k2(h, tmp[0], tmp[1], tmp[2], st[0], st[1], st[2], w, hh, pitch, passes);
+        T = threshold_after(iters, m, T);
+    }
+}
+
+// MGL:1196-1318 coarse-to-fine loop.
+int run_levels(ugsm_handle* h) {
+    const int levels = h->cfg.levels;
+    const int fl = h->cfg.fovea_level;
+    for (int i = levels - 1; i >= 0; i--) {
+        LevelBuf& b = h->lv[i];
+        if (i == levels - 1) {
+            // zero start (the reference reads uninitialised malloc here, MGL:1247)
+            for (int k = 0; k < 3; k++)
+                CK(cudaMemsetAsync(b.st[k], 0, (size_t)b.mpitch * b.mh * sizeof(float), h->stream));
+        } else {
+            LevelBuf& c = h->lv[i + 1];
+            if (h->mode == 0 || i + 1 >= fl) {  // MGL:1279 / 1283-1286
+                launch_k3(h, c.st, c.mw, c.mh, c.mpitch, 0, 0, b.st, b.mw, b.mh, b.mpitch);
+            } else {  // MGL:1290 + 1612-1615: upsample to level fl-2 dims, centre crop
+                int w2 = h->dims.width[fl - 2], h2 = h->dims.height[fl - 2];
+                launch_k3(h, c.st, c.mw, c.mh, c.mpitch, w2 / 2 - c.mw / 2, h2 / 2 - c.mh / 2, b.st, b.mw, b.mh,
+                          b.mpitch);
+            }
+        }
+        run_level(h, b.Lm, b.Rm, b.U, b.st, h->tmp, b.mw, b.mh, b.mpitch, b.iters, b.smooth, i == levels - 1);
+        CK(cudaEventRecord(h->ev[4 + i], h->stream));
+    }
+    return UGSM_OK;
+}
+
+// Whole device-resident pair: pyramid of both images, crops/energy, coarse-to-fine loop.
+int run_pair(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int rows, int cols, size_t step,
+             int mode) {
+    if (!d_rgbL || !d_rgbR) return fail(h, UGSM_ERR_INVALID, "null image pointer");
+    if (step < (size_t)cols * 3) return fail(h, UGSM_ERR_INVALID, "step %zu < cols*3", step);
+    CK(cudaSetDevice(h->device));
+    int rc = set_kernel_attrs(h);
+    if (rc) return rc;
+    rc = prepare_shape(h, rows, cols, mode);
+    if (rc) return rc;
+    h->launches = 0;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    build_pyramid(h, d_rgbL, step, false);
+    build_pyramid(h, d_rgbR, step, true);
+    prepare_levels(h);
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    rc = run_levels(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    CK(cudaGetLastError());
+    return UGSM_OK;
+}
+
+int finish_timing(ugsm_handle* h) {
+    CK(cudaEventSynchronize(h->ev[2]));
+    ugsm_timing& t = h->timing;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]));
+    t.total_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    t.pyramid_ms = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]));
+    t.levels_ms = ms;
+    const int levels = h->cfg.levels;
+    for (int i = levels - 1; i >= 0; i--) {
+        cudaEvent_t prev = (i == levels - 1) ? h->ev[1] : h->ev[4 + i + 1];
+        CK(cudaEventElapsedTime(&ms, prev, h->ev[4 + i]));
+        t.level_ms[i] = ms;
+    }
+    t.launches = h->launches;
+    return UGSM_OK;
+}
+
+int ensure_staging(ugsm_handle* h, size_t rgb_bytes, size_t out_floats) {
+    if (rgb_bytes > h->d_rgb_bytes) {
+        for (int k = 0; k < 2; k++) {
+            if (h->d_rgb[k]) cudaFree(h->d_rgb[k]);
+            h->d_rgb[k] = nullptr;
+        }
+        h->d_rgb_bytes = 0;
+        for (int k = 0; k < 2; k++) CK(cudaMalloc(&h->d_rgb[k], rgb_bytes));
+        h->d_rgb_bytes = rgb_bytes;
+    }
+    if (out_floats > h->d_out_floats) {
+        for (int k = 0; k < 3; k++) {
+            if (h->d_out[k]) cudaFree(h->d_out[k]);
+            h->d_out[k] = nullptr;
+        }
+        h->d_out_floats = 0;
+        for (int k = 0; k < 3; k++) CK(cudaMalloc(&h->d_out[k], out_floats * sizeof(float)));
+        h->d_out_floats = out_floats;
+    }
+    return UGSM_OK;
+}
+
+// Write the results of the last run_pair into dense device planes.
+int emit_full(ugsm_handle* h, float* dH, float* dV, float* dC) {
+    LevelBuf& b = h->lv[0];
+    launch_copy3(h, b.st[0], b.st[1], b.st[2], b.mpitch, dH, dV, dC, b.mw, b.mw, b.mh);
+    CK(cudaGetLastError());
+    return UGSM_OK;
+}
+int emit_stack(ugsm_handle* h, float* sH, float* sV, float* sC) {
+    const int fl = h->cfg.fovea_level;
+    for (int i = 0; i < fl; i++) {  // level-major rows, UG_GPU_matcher.cpp:293-303
+        LevelBuf& b = h->lv[i];
+        size_t off = (size_t)i * b.mw * b.mh;
+        launch_copy3(h, b.st[0], b.st[1], b.st[2], b.mpitch, sH + off, sV + off, sC + off, b.mw, b.mw, b.mh);
+    }
+    CK(cudaGetLastError());
+    return UGSM_OK;
+}
+
+struct TmpDev {  // scoped device allocations for the ugsm_stage_* entry points
+    std::vector<void*> ptrs;
+    ~TmpDev() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <class T>
+    T* alloc(size_t n) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return static_cast<T*>(p);
+    }
+};
+
+// dense host plane -> pitched device plane and back
+cudaError_t up2d(float* d, int pitch, const float* hsrc, int w, int hh, cudaStream_t s) {
+    return cudaMemcpy2DAsync(d, (size_t)pitch * 4, hsrc, (size_t)w * 4, (size_t)w * 4, hh, cudaMemcpyHostToDevice, s);
+}
+cudaError_t down2d(float* hdst, const float* d, int pitch, int w, int hh, cudaStream_t s) {
+    return cudaMemcpy2DAsync(hdst, (size_t)w * 4, d, (size_t)pitch * 4, (size_t)w * 4, hh, cudaMemcpyDeviceToHost, s);
+}
+
+}  // namespace
+
+// =============================================================================== C-ABI
+extern "C" {
+
+const char* ugsm_version(void) { return "ugsm-b200 0.1 (sm_100a)"; }
+
+void ugsm_config_default(ugsm_config* cfg) {
+    if (!cfg) return;
+    cfg->levels = UGSM_MAX_LEVELS;
+    cfg->fovea_level = 7;
+    cfg->device = -1;
+    cfg->iters_cutoff = 22;
+    cfg->smooth_passes = 5;
+    cfg->smooth_passes_fine = 10;
+    cfg->max_iters = 0;
+    cfg->use_graph = 1;
+}
+
+int ugsm_query_dims(const ugsm_config* cfg, int rows, int cols, int mode, ugsm_dims* out) {
+    if (!cfg || !out) return UGSM_ERR_INVALID;
+    return compute_dims(*cfg, rows, cols, mode, out);
+}
+
+int ugsm_create(const ugsm_config* cfg, ugsm_handle** out) {
+    ugsm_handle* h = nullptr;
+    if (!out) return fail(nullptr, UGSM_ERR_INVALID, "out == NULL");
+    *out = nullptr;
+    ugsm_config c;
+    if (cfg)
+        c = *cfg;
+    else
+        ugsm_config_default(&c);
+    if (!validate_cfg(c)) return fail(nullptr, UGSM_ERR_INVALID, "invalid config");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1)
+        return fail(nullptr, UGSM_ERR_NO_DEVICE, "no CUDA device: %s (this library has no CPU fallback)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    int dev = c.device;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    }
+    if (dev >= ndev) return fail(nullptr, UGSM_ERR_INVALID, "device %d out of range (%d devices)", dev, ndev);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess)
+        return fail(nullptr, UGSM_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, UGSM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                    prop.major, prop.minor);
+    h = new ugsm_handle();
+    h->cfg = c;
+    h->device = dev;
+    h->sm_count = prop.multiProcessorCount;
+    make_taps(h->taps);
+    memset(&h->timing, 0, sizeof h->timing);
+    if ((e = cudaSetDevice(dev)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, UGSM_ERR_CUDA, "stream creation: %s", cudaGetErrorString(e));
+    }
+    h->stream = h->own_stream;
+    for (auto& ev : h->ev) {
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) {
+            delete h;
+            return fail(nullptr, UGSM_ERR_CUDA, "event creation: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = h;
+    return UGSM_OK;
+}
+
+int ugsm_destroy(ugsm_handle* h) {
+    if (!h) return UGSM_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    release_shape(h);
+    for (int k = 0; k < 2; k++)
+        if (h->d_rgb[k]) cudaFree(h->d_rgb[k]);
+    for (int k = 0; k < 3; k++)
+        if (h->d_out[k]) cudaFree(h->d_out[k]);
+    for (auto& ev : h->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return UGSM_OK;
+}
+
+const char* ugsm_last_error(const ugsm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ugsm_set_stream(ugsm_handle* h, void* cuda_stream) {
+    if (!h) return UGSM_ERR_INVALID;
+    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return UGSM_OK;
+}
+
+int ugsm_get_timing(const ugsm_handle* h, ugsm_timing* out) {
+    if (!h || !out) return UGSM_ERR_INVALID;
+    *out = h->timing;
+    return UGSM_OK;
+}
+
+int ugsm_match_full_device(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int rows, int cols,
+                           size_t step, float* dH, float* dV, float* dC) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!dH || !dV || !dC) return fail(h, UGSM_ERR_INVALID, "null output pointer");
+    int rc = run_pair(h, d_rgbL, d_rgbR, rows, cols, step, 0);
+    if (rc) return rc;
+    rc = emit_full(h, dH, dV, dC);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->timing.h2d_ms = h->timing.d2h_ms = 0;
+    return finish_timing(h);
+}
+
+int ugsm_match_foveated_device(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int rows, int cols,
+                               size_t step, float* d_stackH, float* d_stackV, float* d_stackC) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!d_stackH || !d_stackV || !d_stackC) return fail(h, UGSM_ERR_INVALID, "null output pointer");
+    int rc = run_pair(h, d_rgbL, d_rgbR, rows, cols, step, 1);
+    if (rc) return rc;
+    rc = emit_stack(h, d_stackH, d_stackV, d_stackC);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->timing.h2d_ms = h->timing.d2h_ms = 0;
+    return finish_timing(h);
+}
+
+static int match_host(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step,
+                      int mode, float* o0, float* o1, float* o2, int* fovW, int* fovH) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!rgbL || !rgbR || !o0 || !o1 || !o2) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+    if (rows < 1 || cols < 1 || step < (size_t)cols * 3) return fail(h, UGSM_ERR_INVALID, "bad rows/cols/step");
+    ugsm_dims d;
+    int rc = compute_dims(h->cfg, rows, cols, mode, &d);
+    if (rc) return fail(h, rc, "invalid shape/config: rows=%d cols=%d mode=%d", rows, cols, mode);
+    CK(cudaSetDevice(h->device));
+    size_t rgb_bytes = step * (size_t)rows;
+    size_t out_floats = mode == 0 ? (size_t)rows * cols : (size_t)d.stack_rows * d.fov_width;
+    rc = ensure_staging(h, rgb_bytes, out_floats);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(cudaMemcpyAsync(h->d_rgb[0], rgbL, rgb_bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_rgb[1], rgbR, rgb_bytes, cudaMemcpyHostToDevice, h->stream));
+    rc = run_pair(h, h->d_rgb[0], h->d_rgb[1], rows, cols, step, mode);
+    if (rc) return rc;
+    rc = mode == 0 ? emit_full(h, h->d_out[0], h->d_out[1], h->d_out[2])
+                   : emit_stack(h, h->d_out[0], h->d_out[1], h->d_out[2]);
+    if (rc) return rc;
+    float* outs[3] = {o0, o1, o2};
+    for (int k = 0; k < 3; k++)
+        CK(cudaMemcpyAsync(outs[k], h->d_out[k], out_floats * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    rc = finish_timing(h);
+    if (rc) return rc;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[3], h->ev[0]));
+    h->timing.h2d_ms = ms;
+    h->timing.d2h_ms = 0;
+    if (fovW) *fovW = d.fov_width;
+    if (fovH) *fovH = d.fov_height;
+    return UGSM_OK;
+}
+
+int ugsm_match_full(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step,
+                    float* H, float* V, float* C) {
+    return match_host(h, rgbL, rgbR, rows, cols, step, 0, H, V, C, nullptr, nullptr);
+}
+
+int ugsm_match_foveated(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step,
+                        float* stackH, float* stackV, float* stackC, int* fovW, int* fovH) {
+    return match_host(h, rgbL, rgbR, rows, cols, step, 1, stackH, stackV, stackC, fovW, fovH);
+}
+
+int ugsm_get_pyramid_level(ugsm_handle* h, int level, float* left3, float* right3) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (h->lv.empty() || level < 0 || level >= (int)h->lv.size())
+        return fail(h, UGSM_ERR_INVALID, "no pyramid level %d (run a match first)", level);
+    CK(cudaSetDevice(h->device));
+    LevelBuf& b = h->lv[level];
+    size_t n = (size_t)b.w * b.h;
+    for (int k = 0; k < 3; k++) {
+        if (left3) CK(down2d(left3 + k * n, b.L[k], b.pitch, b.w, b.h, h->stream));
+        if (right3) CK(down2d(right3 + k * n, b.R[k], b.pitch, b.w, b.h, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return UGSM_OK;
+}
+
+int ugsm_get_fovea_images(ugsm_handle* h, int level, float* left3, float* right3) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (h->lv.empty() || level < 0 || level >= (int)h->lv.size())
+        return fail(h, UGSM_ERR_INVALID, "no level %d (run a match first)", level);
+    CK(cudaSetDevice(h->device));
+    LevelBuf& b = h->lv[level];
+    size_t n = (size_t)b.mw * b.mh;
+    for (int k = 0; k < 3; k++) {
+        if (left3) CK(down2d(left3 + k * n, b.Lm[k], b.mpitch, b.mw, b.mh, h->stream));
+        if (right3) CK(down2d(right3 + k * n, b.Rm[k], b.mpitch, b.mw, b.mh, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return UGSM_OK;
+}
+
+int ugsm_get_level_disparity(ugsm_handle* h, int level, float* H, float* V, float* C) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (h->lv.empty() || level < 0 || level >= (int)h->lv.size())
+        return fail(h, UGSM_ERR_INVALID, "no level %d (run a match first)", level);
+    CK(cudaSetDevice(h->device));
+    LevelBuf& b = h->lv[level];
+    float* outs[3] = {H, V, C};
+    for (int k = 0; k < 3; k++)
+        if (outs[k]) CK(down2d(outs[k], b.st[k], b.mpitch, b.mw, b.mh, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return UGSM_OK;
+}
+
+// ------------------------------------------------------------------- stage entry points
+int ugsm_stage_pyramid(ugsm_handle* h, const uint8_t* rgb, int rows, int cols, size_t step, float* const* out3) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!rgb || !out3 || step < (size_t)cols * 3) return fail(h, UGSM_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    int rc = prepare_shape(h, rows, cols, 0);
+    if (rc) return rc;
+    rc = ensure_staging(h, step * (size_t)rows, 1);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_rgb[0], rgb, step * (size_t)rows, cudaMemcpyHostToDevice, h->stream));
+    build_pyramid(h, h->d_rgb[0], step, false);
+    CK(cudaGetLastError());
+    for (int l = 0; l < h->cfg.levels; l++) {
+        if (!out3[l]) continue;
+        LevelBuf& b = h->lv[l];
+        size_t n = (size_t)b.w * b.h;
+        for (int k = 0; k < 3; k++) CK(down2d(out3[l] + k * n, b.L[k], b.pitch, b.w, b.h, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return UGSM_OK;
+}
+
+int ugsm_stage_correlate(ugsm_handle* h, const float* L3, const float* R3, const float* H, const float* V,
+                         const float* C, int width, int height, float threshold, int first_coarsest, float* Hn,
+                         float* Vn, float* Cn, int32_t* dbg_srcx, int32_t* dbg_srcy, uint8_t* dbg_branch_h,
+                         uint8_t* dbg_branch_v) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!L3 || !R3 || !H || !V || !C || !Hn || !Vn || !Cn || width < 1 || height < 1)
+        return fail(h, UGSM_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    int rc = set_kernel_attrs(h);
+    if (rc) return rc;
+    TmpDev td;
+    int pitch = align_up(width, 32);
+    size_t n = (size_t)width * height, np = (size_t)pitch * height;
+    float* d[15];
+    for (auto& p : d)
+        if (!(p = td.alloc<float>(np))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
+    bool dbg = dbg_srcx && dbg_srcy && dbg_branch_h && dbg_branch_v;
+    int32_t *dsx = nullptr, *dsy = nullptr;
+    uint8_t *dbh = nullptr, *dbv = nullptr;
+    if (dbg) {
+        dsx = td.alloc<int32_t>(n);
+        dsy = td.alloc<int32_t>(n);
+        dbh = td.alloc<uint8_t>(n);
+        dbv = td.alloc<uint8_t>(n);
+        if (!dsx || !dsy || !dbh || !dbv) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
+    }
+    for (int k = 0; k < 3; k++) {
+        CK(up2d(d[k], pitch, L3 + k * n, width, height, h->stream));
+        CK(up2d(d[3 + k], pitch, R3 + k * n, width, height, h->stream));
+    }
+    CK(up2d(d[9], pitch, H, width, height, h->stream));
+    CK(up2d(d[10], pitch, V, width, height, h->stream));
+    CK(up2d(d[11], pitch, C, width, height, h->stream));
+    K1Params p;
+    for (int k = 0; k < 3; k++) {
+        launch_energy(h, d[k], width, height, pitch, d[6 + k]);
+        p.L[k] = d[k];
+        p.R[k] = d[3 + k];
+        p.U[k] = d[6 + k];
+    }
+    p.H = d[9];
+    p.V = d[10];
+    p.C = d[11];
+    p.Hn = d[12];
+    p.Vn = d[13];
+    p.Cn = d[14];
+    p.w = width;
+    p.h = height;
+    p.pitch = pitch;
+    p.T = threshold;
+    p.first_coarsest = first_coarsest ? 1 : 0;
+    p.dbg_srcx = dsx;
+    p.dbg_srcy = dsy;
+    p.dbg_bh = dbh;
+    p.dbg_bv = dbv;
+    p.tp = h->taps;
+    launch_k1(h, p);
+    CK(cudaGetLastError());
+    CK(down2d(Hn, d[12], pitch, width, height, h->stream));
+    CK(down2d(Vn, d[13], pitch, width, height, h->stream));
+    CK(down2d(Cn, d[14], pitch, width, height, h->stream));
+    if (dbg) {
+        CK(cudaMemcpyAsync(dbg_srcx, dsx, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(dbg_srcy, dsy, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(dbg_branch_h, dbh, n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(dbg_branch_v, dbv, n, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return UGSM_OK;
+}
+
+int ugsm_stage_smooth(ugsm_handle* h, float* H, float* V, float* C, int width, int height, int passes) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!H || !V || !C || width < 1 || height < 1 || passes < 0 || passes > 16)
+        return fail(h, UGSM_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    int rc = set_kernel_attrs(h);
+    if (rc) return rc;
+    TmpDev td;
+    int pitch = align_up(width, 32);
+    size_t np = (size_t)pitch * height;
+    float* d[6];
+    for (auto& p : d)
+        if (!(p = td.alloc<float>(np))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
+    float* io[3] = {H, V, C};
+    for (int k = 0; k < 3; k++) CK(up2d(d[k], pitch, io[k], width, height, h->stream));
+    launch_k2(h, d[0], d[1], d[2], d[3], d[4], d[5], width, height, pitch, passes);
+    CK(cudaGetLastError());
+    for (int k = 0; k < 3; k++) CK(down2d(io[k], d[3 + k], pitch, width, height, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return UGSM_OK;
+}
+
+int ugsm_stage_upsample(ugsm_handle* h, const float* H, const float* V, const float* C, int width, int height,
+                        int fine_w, int fine_h, int crop_x, int crop_y, int out_w, int out_h, float* Ho, float* Vo,
+                        float* Co) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!H || !V || !C || !Ho || !Vo || !Co || width < 1 || height < 1 || out_w < 1 || out_h < 1 || crop_x < 0 ||
+        crop_y < 0 || crop_x + out_w > fine_w || crop_y + out_h > fine_h)
+        return fail(h, UGSM_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    TmpDev td;
+    int sp = align_up(width, 32), dp = align_up(out_w, 32);
+    float *s[3], *d[3];
+    for (auto& p : s)
+        if (!(p = td.alloc<float>((size_t)sp * height))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
+    for (auto& p : d)
+        if (!(p = td.alloc<float>((size_t)dp * out_h))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
+    const float* in[3] = {H, V, C};
+    float* out[3] = {Ho, Vo, Co};
+    for (int k = 0; k < 3; k++) CK(up2d(s[k], sp, in[k], width, height, h->stream));
+    launch_k3(h, s, width, height, sp, crop_x, crop_y, d, out_w, out_h, dp);
+    CK(cudaGetLastError());
+    for (int k = 0; k < 3; k++) CK(down2d(out[k], d[k], dp, out_w, out_h, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return UGSM_OK;
+}
+
+int ugsm_stage_match_level(ugsm_handle* h, const float* L3, const float* R3, float* H, float* V, float* C, int width,
+                           int height, int iters, int passes, int coarsest) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!L3 || !R3 || !H || !V || !C || width < 1 || height < 1 || iters < 0 || passes < 0 || passes > 16)
+        return fail(h, UGSM_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    int rc = set_kernel_attrs(h);
+    if (rc) return rc;
+    TmpDev td;
+    int pitch = align_up(width, 32);
+    size_t n = (size_t)width * height, np = (size_t)pitch * height;
+    float* d[15];
+    for (auto& p : d)
+        if (!(p = td.alloc<float>(np))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
+    float* io[3] = {H, V, C};
+    for (int k = 0; k < 3; k++) {
+        CK(up2d(d[k], pitch, L3 + k * n, width, height, h->stream));
+        CK(up2d(d[3 + k], pitch, R3 + k * n, width, height, h->stream));
+        CK(up2d(d[9 + k], pitch, io[k], width, height, h->stream));
+    }
+    for (int k = 0; k < 3; k++) launch_energy(h, d[k], width, height, pitch, d[6 + k]);
+    run_level(h, d, d + 3, d + 6, d + 9, d + 12, width, height, pitch, iters, passes, coarsest != 0);
+    CK(cudaGetLastError());
+    for (int k = 0; k < 3; k++) CK(down2d(io[k], d[9 + k], pitch, width, height, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return UGSM_OK;
+}
+
+// ------------------------------------------------------------------- micro-benchmarks
+__global__ void k_fill_synth(float* p, size_t n, float lo, float hi, uint32_t seed) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x = (uint32_t)i * 2654435761u + seed;
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    p[i] = lo + (hi - lo) * (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+
+int ugsm_bench_correlate(ugsm_handle* h, int width, int height, int reps, float* avg_ms) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (width < 1 || height < 1 || reps < 1 || !avg_ms) return fail(h, UGSM_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    int rc = set_kernel_attrs(h);
+    if (rc) return rc;
+    TmpDev td;
+    int pitch = align_up(width, 32);
+    size_t np = (size_t)pitch * height;
+    float* d[15];
+    for (auto& p : d)
+        if (!(p = td.alloc<float>(np))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
+    int blocks = (int)((np + 255) / 256);
+    for (int k = 0; k < 6; k++) k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[k], np, 16.f, 240.f, 17u * k + 1);
+    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[9], np, -2.f, 2.f, 101u);
+    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[10], np, -1.f, 1.f, 102u);
+    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[11], np, 0.3f, 1.f, 103u);
+    K1Params p;
+    for (int k = 0; k < 3; k++) {
+        launch_energy(h, d[k], width, height, pitch, d[6 + k]);
+        p.L[k] = d[k];
+        p.R[k] = d[3 + k];
+        p.U[k] = d[6 + k];
+    }
+    p.H = d[9];
+    p.V = d[10];
+    p.C = d[11];
+    p.Hn = d[12];
+    p.Vn = d[13];
+    p.Cn = d[14];
+    p.w = width;
+    p.h = height;
+    p.pitch = pitch;
+    p.T = 1.0f;
+    p.first_coarsest = 0;
+    p.dbg_srcx = p.dbg_srcy = nullptr;
+    p.dbg_bh = p.dbg_bv = nullptr;
+    p.tp = h->taps;
+    for (int i = 0; i < 3; i++) launch_k1(h, p);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < reps; i++) launch_k1(h, p);
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaGetLastError());
+    *avg_ms = ms / reps;
+    return UGSM_OK;
+}
+
+int ugsm_bench_smooth(ugsm_handle* h, int width, int height, int passes, int reps, float* avg_ms) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (width < 1 || height < 1 || reps < 1 || passes < 0 || passes > 16 || !avg_ms)
+        return fail(h, UGSM_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    int rc = set_kernel_attrs(h);
+    if (rc) return rc;
+    TmpDev td;
+    int pitch = align_up(width, 32);
+    size_t np = (size_t)pitch * height;
+    float* d[6];
+    for (auto& p : d)
+        if (!(p = td.alloc<float>(np))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
+    int blocks = (int)((np + 255) / 256);
+    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[0], np, -2.f, 2.f, 101u);
+    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[1], np, -1.f, 1.f, 102u);
+    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[2], np, 0.3f, 1.f, 103u);
+    for (int i = 0; i < 3; i++) launch_k2(h, d[0], d[1], d[2], d[3], d[4], d[5], width, height, pitch, passes);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < reps; i++) launch_k2(h, d[0], d[1], d[2], d[3], d[4], d[5], width, height, pitch, passes);
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaGetLastError());
+    *avg_ms = ms / reps;
+    return UGSM_OK;
+}
+
+}  // extern "C"
