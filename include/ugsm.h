@@ -37,6 +37,7 @@ extern "C" {
 #endif
 
 #define UGSM_MAX_LEVELS 14 /* MAX_LEVEL, MatchLib_common.h:13 */
+#define UGSM_TIMED_LEVELS 4
 
 enum {
     UGSM_OK = 0,
@@ -56,7 +57,7 @@ typedef struct ugsm_config {
     int32_t smooth_passes;      /* smoothtime=5, MatchGPULib.cpp:38 */
     int32_t smooth_passes_fine; /* 10 on the two finest levels, MatchGPULib.cpp:2259-2261 */
     int32_t max_iters;          /* 0 = reference schedule; >0 caps iterations per level (tests only) */
-    int32_t use_graph;          /* 1 = replay the level loop through CUDA graphs (default) */
+    int32_t use_graph;          /* 1 = replay the per-pair launch sequence through a CUDA graph; 0 = plain stream launches */
 } ugsm_config;
 
 typedef struct ugsm_dims {
@@ -80,6 +81,11 @@ typedef struct ugsm_timing {
     float h2d_ms, d2h_ms;
     int32_t launches;    /* kernels launched by the last call */
     float level_ms[UGSM_MAX_LEVELS];
+    /* Sum of the K1 (correlate) / K2 (smooth) launch durations per level, from CUDA events
+     * recorded around every launch on the handle's stream; measured on the UGSM_TIMED_LEVELS
+     * finest levels only (the others stay 0 so that events never pace the tiny kernels). */
+    float k1_ms[UGSM_MAX_LEVELS];
+    float k2_ms[UGSM_MAX_LEVELS];
 } ugsm_timing;
 
 typedef struct ugsm_handle ugsm_handle;

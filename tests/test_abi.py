@@ -28,7 +28,7 @@ def test_exports_every_declared_symbol(capi):
 def test_struct_layout_matches_header(capi):
     assert C.sizeof(capi.Config) == 8 * 4
     assert C.sizeof(capi.Dims) == 4 + 6 * 14 * 4 + 3 * 4 + 8
-    assert C.sizeof(capi.Timing) == 5 * 4 + 4 + 14 * 4
+    assert C.sizeof(capi.Timing) == 5 * 4 + 4 + 3 * 14 * 4
 
 
 def test_defaults_are_reference_constants(capi):

@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libugsm.so")
 MAX_LEVELS = 14
+TIMED_LEVELS = 4
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM = 0, 1, 2, 3, 4
 
@@ -63,6 +64,8 @@ class Timing(C.Structure):
         ("d2h_ms", C.c_float),
         ("launches", C.c_int32),
         ("level_ms", C.c_float * MAX_LEVELS),
+        ("k1_ms", C.c_float * MAX_LEVELS),
+        ("k2_ms", C.c_float * MAX_LEVELS),
     ]
 
 

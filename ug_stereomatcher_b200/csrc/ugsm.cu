@@ -72,6 +72,11 @@ struct ugsm_handle {
     size_t d_out_floats = 0;
 
     cudaEvent_t ev[4 + UGSM_MAX_LEVELS] = {};
+    // per-launch events of the UGSM_TIMED_LEVELS finest levels: 3 per iteration (before K1, between, after K2)
+    static constexpr int KEV_MAX = 3 * 64;
+    cudaEvent_t kev[KEV_MAX] = {};
+    int kev_used = 0;
+    int kev_level[64] = {};
     ugsm_timing timing;
     int launches = 0;
     bool k_attr_set = false;
@@ -177,35 +182,32 @@ int compute_dims(const ugsm_config& c, int rows, int cols, int mode, ugsm_dims* 
 
 // ------------------------------------------------------------------ kernel launchers
 constexpr int K1_TH = 16;
-constexpr int K2_TW = 64, K2_TH = 32;
+constexpr int K1S_TH = 8;
+constexpr long K1_SMALL_PIXELS = 400000;  // levels below this use k1_correlate_small
+constexpr int K2_MAX_BH = 64;  // region rows (tile + 2 halos): 2*3*64*128*4 B = 192 KB of shared memory
 
-size_t k2_smem_bytes(int passes) {
-    int R = passes + 1;
-    return (size_t)2 * 3 * (K2_TW + 2 * R) * (K2_TH + 2 * R) * sizeof(float);
-}
+size_t k2_smem_bytes(int bh) { return (size_t)2 * 3 * K2_BW * bh * sizeof(float); }
 
 int set_kernel_attrs(ugsm_handle* h) {
     if (h->k_attr_set) return UGSM_OK;
     CK(cudaFuncSetAttribute(k1_correlate<4, K1_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(K1Smem<4, K1_TH>)));
-    CK(cudaFuncSetAttribute(k1_correlate<1, K1_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(K1Smem<1, K1_TH>)));
-    CK(cudaFuncSetAttribute(k2_smooth_box<K2_TW, K2_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)k2_smem_bytes(16)));
+    CK(cudaFuncSetAttribute(k2_smooth_box, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)k2_smem_bytes(K2_MAX_BH)));
     h->k_attr_set = true;
     return UGSM_OK;
 }
 
 void launch_k1(ugsm_handle* h, const K1Params& p) {
-    // Wide levels: 4-warp CTAs (120 columns); narrow ones: 1-warp CTAs so that the few
-    // tiles there are spread over more SMs.
-    long tiles4 = (long)div_up(p.w, 120) * div_up(p.h, K1_TH);
-    if (tiles4 >= 2L * h->sm_count) {
+    // Large levels: 4-warp CTAs (120 columns x 16 rows), channels in sequence.  Small levels:
+    // 30 x 8 tiles with one warp per colour channel, so that the few tiles there spread over
+    // more SMs and the dependent chain per launch is short.
+    if ((long)p.w * p.h >= K1_SMALL_PIXELS) {
         dim3 grid(div_up(p.w, 120), div_up(p.h, K1_TH));
         k1_correlate<4, K1_TH><<<grid, 128, sizeof(K1Smem<4, K1_TH>), h->stream>>>(p);
     } else {
-        dim3 grid(div_up(p.w, 30), div_up(p.h, K1_TH));
-        k1_correlate<1, K1_TH><<<grid, 32, sizeof(K1Smem<1, K1_TH>), h->stream>>>(p);
+        dim3 grid(div_up(p.w, 30), div_up(p.h, K1S_TH));
+        k1_correlate_small<K1S_TH><<<grid, 96, 0, h->stream>>>(p);
     }
     h->launches++;
 }
@@ -224,8 +226,18 @@ void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci
     p.pitch = pitch;
     p.passes = passes;
     p.a1 = h->taps.a[1];
-    dim3 grid(div_up(w, K2_TW), div_up(hh, K2_TH));
-    k2_smooth_box<K2_TW, K2_TH><<<grid, 256, k2_smem_bytes(passes), h->stream>>>(p);
+    const int R = passes + 1;
+    p.hpad = align_up(R, 4);
+    const int twu = K2_BW - 2 * p.hpad;
+    // Tile height: as tall as shared memory allows on big levels (less halo redundancy); shorter on
+    // small levels so that there are at least ~2 CTAs per SM.
+    int th = K2_MAX_BH - 2 * R;
+    const int cols = div_up(w, twu);
+    while (th > 8 && (long)cols * div_up(hh, th) < 2L * h->sm_count) th = (th + 1) / 2;
+    if (th > hh) th = hh;
+    p.th = th;
+    dim3 grid(cols, div_up(hh, th));
+    k2_smooth_box<<<grid, K2_NWARP * 32, k2_smem_bytes(th + 2 * R), h->stream>>>(p);
     h->launches++;
 }
 
@@ -378,9 +390,16 @@ void prepare_levels(ugsm_handle* h) {
 
 // MGL:1662-2489: `iters` iterations of K1 (correlate/fit/blend) + K2 (smooth/box).
 void run_level(ugsm_handle* h, float* const L[3], float* const R[3], float* const U[3], float* const st[3],
-               float* const tmp[3], int w, int hh, int pitch, int iters, int passes, bool coarsest) {
+               float* const tmp[3], int w, int hh, int pitch, int iters, int passes, bool coarsest,
+               int timed_level = -1) {
     float T = 1.0f;  // MGL:1673
     for (int m = 1; m <= iters; m++) {
+        int slot = -1;
+        if (timed_level >= 0 && h->kev_used < 64) {
+            slot = h->kev_used++;
+            h->kev_level[slot] = timed_level;
+            cudaEventRecord(h->kev[3 * slot], h->stream);
+        }
         K1Params p;
         for (int k = 0; k < 3; k++) {
             p.L[k] = L[k];
@@ -404,7 +423,9 @@ void run_level(ugsm_handle* h, float* const L[3], float* const R[3], float* cons
         p.dbg_bv = nullptr;
         p.tp = h->taps;
         launch_k1(h, p);
+        if (slot >= 0) cudaEventRecord(h->kev[3 * slot + 1], h->stream);
         launch_k2(h, tmp[0], tmp[1], tmp[2], st[0], st[1], st[2], w, hh, pitch, passes);
+        if (slot >= 0) cudaEventRecord(h->kev[3 * slot + 2], h->stream);
         T = threshold_after(iters, m, T);
     }
 }
@@ -429,7 +450,8 @@ int run_levels(ugsm_handle* h) {
                           b.mpitch);
             }
         }
-        run_level(h, b.Lm, b.Rm, b.U, b.st, h->tmp, b.mw, b.mh, b.mpitch, b.iters, b.smooth, i == levels - 1);
+        run_level(h, b.Lm, b.Rm, b.U, b.st, h->tmp, b.mw, b.mh, b.mpitch, b.iters, b.smooth, i == levels - 1,
+                  i < UGSM_TIMED_LEVELS ? i : -1);
         CK(cudaEventRecord(h->ev[4 + i], h->stream));
     }
     return UGSM_OK;
@@ -446,6 +468,7 @@ int run_pair(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int r
     rc = prepare_shape(h, rows, cols, mode);
     if (rc) return rc;
     h->launches = 0;
+    h->kev_used = 0;
     CK(cudaEventRecord(h->ev[0], h->stream));
     build_pyramid(h, d_rgbL, step, false);
     build_pyramid(h, d_rgbR, step, true);
@@ -475,6 +498,13 @@ int finish_timing(ugsm_handle* h) {
         t.level_ms[i] = ms;
     }
     t.launches = h->launches;
+    for (int i = 0; i < UGSM_MAX_LEVELS; i++) t.k1_ms[i] = t.k2_ms[i] = 0.f;
+    for (int s = 0; s < h->kev_used; s++) {
+        CK(cudaEventElapsedTime(&ms, h->kev[3 * s], h->kev[3 * s + 1]));
+        t.k1_ms[h->kev_level[s]] += ms;
+        CK(cudaEventElapsedTime(&ms, h->kev[3 * s + 1], h->kev[3 * s + 2]));
+        t.k2_ms[h->kev_level[s]] += ms;
+    }
     return UGSM_OK;
 }
 
@@ -556,7 +586,7 @@ void ugsm_config_default(ugsm_config* cfg) {
     cfg->smooth_passes = 5;
     cfg->smooth_passes_fine = 10;
     cfg->max_iters = 0;
-    cfg->use_graph = 1;
+    cfg->use_graph = 0;
 }
 
 int ugsm_query_dims(const ugsm_config* cfg, int rows, int cols, int mode, ugsm_dims* out) {
@@ -608,6 +638,12 @@ int ugsm_create(const ugsm_config* cfg, ugsm_handle** out) {
             return fail(nullptr, UGSM_ERR_CUDA, "event creation: %s", cudaGetErrorString(e));
         }
     }
+    for (auto& ev : h->kev) {
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) {
+            delete h;
+            return fail(nullptr, UGSM_ERR_CUDA, "event creation: %s", cudaGetErrorString(e));
+        }
+    }
     *out = h;
     return UGSM_OK;
 }
@@ -622,6 +658,8 @@ int ugsm_destroy(ugsm_handle* h) {
     for (int k = 0; k < 3; k++)
         if (h->d_out[k]) cudaFree(h->d_out[k]);
     for (auto& ev : h->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->kev)
         if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
