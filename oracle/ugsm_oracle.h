@@ -14,11 +14,16 @@
  * for sm_100a) are written as explicit fmaf()/fma() here and nothing
  * else may be contracted (build with -ffp-contract=off).
  *
- * Pinning status: the reference ships no golden vectors or tests.
- * The oracle is pinned against (a) the reference's own CPU convolution
- * (convolutionSeparable_gold.cpp, compiled in place into oracle/_ref/) and (b) outputs
- * of the unmodified reference CUDA sources built through a compat shim and run on a
- * B200 (tests/golden/refcuda_*.npz, generated by oracle/refbuild/).  See DESIGN.md.
+ * Pinning status: PINNED.  The reference ships no golden vectors or tests (SURVEY.md
+ * section 4), so the pins were made here: (a) the reference's own CPU convolution
+ * (convolutionSeparable_gold.cpp, compiled in place into oracle/_ref/) and (b) outputs of
+ * the UNMODIFIED reference CUDA sources, built for sm_100a through the compat shims in
+ * oracle/refbuild/ and run on a B200: MatchGPULib::matchlevel (2- and 22-iteration
+ * schedules, coarsest-level variant), convolutionGPU, subsampledimageGPU and subsampleDisp
+ * at tile-aligned sizes -- this oracle reproduces every one of them BIT FOR BIT
+ * (tests/golden/refcuda_stages.npz, tests/test_refcuda_golden.py).  The reference's full
+ * 14-level run is not a usable bit-oracle (out-of-bounds writes at partial tiles), see
+ * DESIGN.md section 3.
  */
 #ifndef UGSM_ORACLE_H
 #define UGSM_ORACLE_H

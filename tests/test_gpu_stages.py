@@ -110,3 +110,37 @@ def test_match_level_bit_exact(gpu, oracle, shape, iters, passes, coarsest):
     want = oracle.match_level(L3, R3, H, V, C, iters, passes, coarsest)
     for g, w, n in zip(got, want, "HVC"):
         _assert_same(g, w, "match_level %s %dx%d" % (n, cols, rows))
+
+
+def test_match_level_bit_exact_vs_live_reference_cuda(gpu, tmp_path):
+    """This repo's CUDA path vs the UNMODIFIED reference CUDA code (oracle/_ref/refcuda_stage, built from
+    /root/reference by oracle/refbuild/) run live on the same GPU, at a tile-aligned size where the
+    reference has no out-of-bounds accidents: bit-exact, no oracle in between."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "refcuda_stage")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/refcuda_stage not built (reference checkout absent at build time)")
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    import make_refcuda_stage_golden as gen
+
+    L3, R3, H0, V0, C0 = gen.stage_inputs()
+    W, H = gen.W, gen.H
+    fin, fout = str(tmp_path / "in.f32"), str(tmp_path / "out.f32")
+    for name, level, iters, passes, coarsest in gen.LEVEL_CASES:
+        if coarsest:
+            h0 = np.zeros_like(H0)
+            v0, c0 = h0.copy(), h0.copy()
+        else:
+            h0, v0, c0 = H0, V0, C0
+        np.concatenate([L3.ravel(), R3.ravel(), h0.ravel(), v0.ravel(), c0.ravel()]).astype(np.float32).tofile(fin)
+        p = subprocess.run([exe, "level", str(W), str(H), str(level), fin, fout], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, timeout=600)
+        assert p.returncode == 0, p.stdout.decode(errors="ignore")[-2000:]
+        ref = np.fromfile(fout, np.float32).reshape(3, H, W)
+        got = gpu.stage_match_level(L3, R3, h0, v0, c0, iters, passes, coarsest)
+        for g, r, n in zip(got, ref, "HVC"):
+            _assert_same(g, r, "%s %s vs live reference CUDA" % (name, n))

@@ -1,0 +1,85 @@
+"""CPU tests (-m "not gpu"): pin the oracle against outputs of the UNMODIFIED reference CUDA code.
+
+tests/golden/refcuda_stages.npz was produced on a B200 by tests/golden/make_refcuda_stage_golden.py, which
+drives the reference's own public methods (MatchGPULib::matchlevel, convolutionGPU, subsampledimageGPU,
+subsampleDisp -- compiled in place from /root/reference through oracle/refbuild/'s compat shims) at
+tile-aligned sizes where the reference has no out-of-bounds accidents.  The oracle must reproduce those
+outputs bit for bit; the -m gpu tests then hold the CUDA path bit-exact to the oracle.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_refcuda_stage_golden as gen  # noqa: E402  (the generating script; shares stage_inputs())
+
+GOLD = os.path.join(HERE, "golden", "refcuda_stages.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def inputs():
+    return gen.stage_inputs()
+
+
+@pytest.mark.parametrize("case", gen.LEVEL_CASES, ids=[c[0] for c in gen.LEVEL_CASES])
+def test_matchlevel_bit_exact_vs_reference_cuda(oracle, gold, inputs, case):
+    """MatchGPULib::matchlevel (MatchGPULib.cpp:1662-2489): finest-level schedule (2 iterations, S=10),
+    mid-level schedule (22 iterations, S=5, threshold schedule) and the coarsest-level variant."""
+    name, _level, iters, passes, coarsest = case
+    L3, R3, H0, V0, C0 = inputs
+    if coarsest:
+        H0 = np.zeros_like(H0)
+        V0, C0 = H0.copy(), H0.copy()
+    got = np.stack(oracle.match_level(L3, R3, H0, V0, C0, iters, passes, coarsest))
+    ref = gold[name]
+    assert got.shape == ref.shape
+    assert np.isfinite(ref).all()
+    assert (got == ref).all(), "%s: %d px differ, max %g" % (name, int((got != ref).sum()), float(np.abs(got - ref).max()))
+
+
+def test_zero_border_conv_bit_exact_vs_reference_cuda(oracle, gold, inputs):
+    """MatchGPULib::convolutionGPU (convolutionRowsKernel + convolutionColumnsKernel, MatchLib.cu:71-305)."""
+    g, _ = oracle.taps()
+    got = oracle.conv_cols_zero(oracle.conv_rows_zero(inputs[0][0], g), g)
+    assert (got == gold["conv"]).all()
+
+
+def test_decimate_bit_exact_vs_reference_cuda(oracle, gold, inputs):
+    """MatchGPULib::subsampledimageGPU (subsampleKernel, MatchLib.cu:311-339) with both scale factors."""
+    L0 = inputs[0][0]
+    d2 = gold["decim2"]
+    assert (oracle.decimate(L0, 2.0, d2.shape[1], d2.shape[0]) == d2).all()
+    ds = gold["decim_sqrt2"]
+    assert (oracle.decimate(L0, float(np.float32(1.41421356)), ds.shape[1], ds.shape[0]) == ds).all()
+
+
+def test_upsample_disp_bit_exact_vs_reference_cuda(oracle, gold, inputs):
+    """MatchGPULib::subsampleDisp (subsampleDispKernel, MatchLib.cu:372-401): all three planes x sqrt2."""
+    _, _, H0, V0, C0 = inputs
+    ref = gold["updisp"]
+    got = np.stack(oracle.upsample_state(H0, V0, C0, ref.shape[2], ref.shape[1]))
+    assert (got == ref).all()
+
+
+def test_recorded_full_pipeline_statistics_are_present():
+    """The full 14-level pipeline of the reference build is NOT a usable bit-oracle: at widths that are not
+    multiples of 128 / heights not multiples of 64 its shared-memory convolutions write garbage into the
+    first 15 columns of the next row (recorded: tests/golden/refcuda_stages_stats.json, 'unaligned_*').
+    This test only checks that the evidence files exist and say what DESIGN.md quotes."""
+    import json
+
+    st = json.load(open(os.path.join(HERE, "golden", "refcuda_stages_stats.json")))
+    assert st["level_i6_H"]["pct_bit_equal"] == 100.0 and st["conv"]["pct_bit_equal"] == 100.0
+    un = st["unaligned_conv_250x120"]
+    assert un["pct_bit_equal"] < 100.0 and set(un["differing_columns"]) <= set(range(0, 15)) | {248, 249}
+    assert st["unaligned_level_i0_250x120"]["pct_bit_equal_interior40"] == 100.0
+    full = json.load(open(os.path.join(HERE, "golden", "refcuda_1232x816_stats.json")))
+    assert full["gpu_vs_oracle_bit_equal_H"] and full["gpu_vs_oracle_bit_equal_V"] and full["gpu_vs_oracle_bit_equal_C"]
