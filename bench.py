@@ -177,18 +177,14 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
 
-    from ug_stereomatcher_b200 import capi, synth
+    from ug_stereomatcher_b200 import capi, dp, synth
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = dp.env_rank()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    dp.init("nccl", dev)
 
     def barrier():
         if world > 1:
@@ -246,11 +242,7 @@ def run_gpu(args):
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
-    tt = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_max = float(tt.item())
+    ms_max = dp.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
     last = h.timing()
 
     # ---- end to end through the host-buffer C-ABI call ---------------------------------------
@@ -262,11 +254,7 @@ def run_gpu(args):
         host_step(i)
     e1.record(stream)
     barrier()
-    e2e_ms = e0.elapsed_time(e1) / args.steps
-    tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(tt.item())
+    e2e_ms_max = dp.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
 
     # result sanity (not parity: tests/ do that): finite and close to the synthetic ground truth
     _, _, dH, dV = synth.make_pair(COLS, ROWS, rank * pool + ((args.steps - 1) % pool))
@@ -280,14 +268,14 @@ def run_gpu(args):
         ach = K1_BYTES_PER_PIXEL * COLS * ROWS / (k1_avg * 1e-3) / 1e9 if k1_avg > 0 else 0.0
         cb = cpu_sample() if world == 1 else None
         line = {
-            "metric": METRIC, "value": world * 1e3 / ms_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": dp.throughput(1, world, ms_max), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (world * 1e3 / ms_max) / 0.1,  # 10 s/pair = 0.1 pairs/s (GTX-class GPU, README.md:15)
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "parallelism": "pair-level data parallel x%d" % world,
                        "l2": "inputs larger than L2: per-pair working set ~2.3 GB vs 126 MB L2; a pool of %d distinct pairs per GPU is cycled" % pool,
                        "levels": 14, "pixel_iterations": PIXEL_ITERS_16MP, "sanity_epe_h_px": epe, "finite": finite},
-            "e2e": {"value": world * 1e3 / e2e_ms_max, "unit": UNIT, "ms_per_pair": e2e_ms_max,
+            "e2e": {"value": dp.throughput(1, world, e2e_ms_max), "unit": UNIT, "ms_per_pair": e2e_ms_max,
                     "h2d_bytes_per_step": 2 * ROWS * step_bytes, "d2h_bytes_per_step": 3 * ROWS * COLS * 4},
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
