@@ -165,6 +165,8 @@ int ugsm_stage_match_level(ugsm_handle* h, const float* L3, const float* R3, flo
  * returns the average per-launch time from CUDA events on the handle's stream. */
 int ugsm_bench_correlate(ugsm_handle* h, int width, int height, int reps, float* avg_ms);
 int ugsm_bench_smooth(ugsm_handle* h, int width, int height, int passes, int reps, float* avg_ms);
+/* Launch floor of the stream: average time of `reps` back-to-back empty kernel launches. */
+int ugsm_bench_null(ugsm_handle* h, int reps, float* avg_ms);
 
 const char* ugsm_version(void);
 

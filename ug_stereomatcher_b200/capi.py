@@ -22,7 +22,7 @@ SYMBOLS = [
     "ugsm_match_full", "ugsm_match_foveated", "ugsm_match_full_device", "ugsm_match_foveated_device",
     "ugsm_get_fovea_images", "ugsm_get_pyramid_level", "ugsm_get_level_disparity", "ugsm_get_timing",
     "ugsm_stage_pyramid", "ugsm_stage_correlate", "ugsm_stage_smooth", "ugsm_stage_upsample",
-    "ugsm_stage_match_level", "ugsm_bench_correlate", "ugsm_bench_smooth", "ugsm_version",
+    "ugsm_stage_match_level", "ugsm_bench_correlate", "ugsm_bench_smooth", "ugsm_bench_null", "ugsm_version",
 ]
 
 
@@ -114,6 +114,7 @@ def lib():
         L.ugsm_stage_match_level.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i]
         L.ugsm_bench_correlate.argtypes = [vp, i, i, i, C.POINTER(C.c_float)]
         L.ugsm_bench_smooth.argtypes = [vp, i, i, i, i, C.POINTER(C.c_float)]
+        L.ugsm_bench_null.argtypes = [vp, i, C.POINTER(C.c_float)]
         _LIB = L
     return _LIB
 
@@ -292,6 +293,11 @@ class Handle:
     def bench_correlate(self, width, height, reps=10):
         ms = C.c_float()
         self._ck(lib().ugsm_bench_correlate(self._h, width, height, reps, C.byref(ms)))
+        return ms.value
+
+    def bench_null(self, reps=100):
+        ms = C.c_float()
+        self._ck(lib().ugsm_bench_null(self._h, reps, C.byref(ms)))
         return ms.value
 
     def bench_smooth(self, width, height, passes, reps=10):

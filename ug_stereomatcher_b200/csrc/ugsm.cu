@@ -80,6 +80,7 @@ struct ugsm_handle {
     ugsm_timing timing;
     int launches = 0;
     bool k_attr_set = false;
+    int k1_nw = 2;
 };
 
 namespace {
@@ -184,6 +185,7 @@ int compute_dims(const ugsm_config& c, int rows, int cols, int mode, ugsm_dims* 
 constexpr int K1_TH = 16;
 constexpr int K1S_TH = 8;
 constexpr long K1_SMALL_PIXELS = 400000;  // levels below this use k1_correlate_small
+constexpr long K2_SMALL_PIXELS = 700000;  // levels below this use k2_smooth_box_small
 constexpr int K2_MAX_BH = 64;  // region rows (tile + 2 halos): 2*3*64*128*4 B = 192 KB of shared memory
 
 size_t k2_smem_bytes(int bh) { return (size_t)2 * 3 * K2_BW * bh * sizeof(float); }
@@ -192,6 +194,9 @@ int set_kernel_attrs(ugsm_handle* h) {
     if (h->k_attr_set) return UGSM_OK;
     CK(cudaFuncSetAttribute(k1_correlate<4, K1_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(K1Smem<4, K1_TH>)));
+    CK(cudaFuncSetAttribute(k1_correlate<2, K1_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(K1Smem<2, K1_TH>)));
+    if (const char* e = getenv("UGSM_K1_NW")) h->k1_nw = atoi(e);  // tuning override: warps per K1 CTA (2 or 4)
     CK(cudaFuncSetAttribute(k2_smooth_box, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)k2_smem_bytes(K2_MAX_BH)));
     h->k_attr_set = true;
@@ -202,7 +207,10 @@ void launch_k1(ugsm_handle* h, const K1Params& p) {
     // Large levels: 4-warp CTAs (120 columns x 16 rows), channels in sequence.  Small levels:
     // 30 x 8 tiles with one warp per colour channel, so that the few tiles there spread over
     // more SMs and the dependent chain per launch is short.
-    if ((long)p.w * p.h >= K1_SMALL_PIXELS) {
+    if ((long)p.w * p.h >= K1_SMALL_PIXELS && h->k1_nw == 2) {
+        dim3 grid(div_up(p.w, 60), div_up(p.h, K1_TH));
+        k1_correlate<2, K1_TH><<<grid, 64, sizeof(K1Smem<2, K1_TH>), h->stream>>>(p);
+    } else if ((long)p.w * p.h >= K1_SMALL_PIXELS) {
         dim3 grid(div_up(p.w, 120), div_up(p.h, K1_TH));
         k1_correlate<4, K1_TH><<<grid, 128, sizeof(K1Smem<4, K1_TH>), h->stream>>>(p);
     } else {
@@ -227,6 +235,16 @@ void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci
     p.passes = passes;
     p.a1 = h->taps.a[1];
     const int R = passes + 1;
+    if ((long)w * hh < K2_SMALL_PIXELS && K2S_T + 2 * R <= 32) {
+        // small levels: 16x16 tiles, one thread per region cell (latency-oriented)
+        p.th = K2S_T;
+        p.hpad = R;
+        const int side = K2S_T + 2 * R;
+        dim3 grid(div_up(w, K2S_T), div_up(hh, K2S_T));
+        k2_smooth_box_small<<<grid, align_up(side * side, 32), 0, h->stream>>>(p);
+        h->launches++;
+        return;
+    }
     p.hpad = align_up(R, 4);
     const int twu = K2_BW - 2 * p.hpad;
     // Tile height: as tall as shared memory allows on big levels (less halo redundancy); shorter on
@@ -249,9 +267,15 @@ void launch_k3(ugsm_handle* h, float* const src[3], int w, int hh, int spitch, i
     h->launches++;
 }
 
-void launch_energy(ugsm_handle* h, const float* L, int w, int hh, int pitch, float* U) {
-    dim3 block(32, 8), grid(div_up(w, 32), div_up(hh, 8));
-    k0_left_energy<<<grid, block, 0, h->stream>>>(L, w, hh, pitch, U, h->taps);
+// U = colT(rowT(L^2)) for `n` planes of equal dims in one launch.
+void launch_energy(ugsm_handle* h, const float* const* L, float* const* U, int n, int w, int hh, int pitch) {
+    K0Planes pl;
+    for (int k = 0; k < 6; k++) {
+        pl.src[k] = L[k < n ? k : 0];
+        pl.dst[k] = U[k < n ? k : 0];
+    }
+    dim3 grid(div_up(w, 32), div_up(hh, 32), n);
+    k0_sep5<0, true, true><<<grid, 256, 0, h->stream>>>(pl, w, hh, pitch, w, hh, pitch, 1.0f, h->taps);
     h->launches++;
 }
 
@@ -261,15 +285,21 @@ void launch_unpack(ugsm_handle* h, const uint8_t* rgb, size_t step, int w, int h
     h->launches++;
 }
 
-void launch_blur_decimate(ugsm_handle* h, int mode, const float* src, int w, int hh, int spitch, float* dst, int w2,
-                          int h2, int dpitch) {
-    dim3 block(32, 8), grid(div_up(w2, 32), div_up(h2, 8));
+// Fused blur + decimate of `n` planes of equal dims in one launch (mode 0: sqrt2 NN, mode 1: odd samples).
+void launch_blur_decimate(ugsm_handle* h, int mode, const float* const* src, float* const* dst, int n, int w, int hh,
+                          int spitch, int w2, int h2, int dpitch) {
+    K0Planes pl;
+    for (int k = 0; k < 6; k++) {
+        pl.src[k] = src[k < n ? k : 0];
+        pl.dst[k] = dst[k < n ? k : 0];
+    }
+    dim3 grid(div_up(w2, 32), div_up(h2, 32), n);
     if (mode == 0) {
         float s = SCALE_D;  // MGL:1083
-        k0_blur_decimate<0><<<grid, block, 0, h->stream>>>(src, w, hh, spitch, dst, w2, h2, dpitch, s, h->taps);
+        k0_sep5<2, false, false><<<grid, 256, 0, h->stream>>>(pl, w, hh, spitch, w2, h2, dpitch, s, h->taps);
     } else {
         float s = 0.000 + (int)(SCALE_D * SCALE_D + 0.5);  // MGL:1090
-        k0_blur_decimate<1><<<grid, block, 0, h->stream>>>(src, w, hh, spitch, dst, w2, h2, dpitch, s, h->taps);
+        k0_sep5<1, false, false><<<grid, 256, 0, h->stream>>>(pl, w, hh, spitch, w2, h2, dpitch, s, h->taps);
     }
     h->launches++;
 }
@@ -353,20 +383,32 @@ int prepare_shape(ugsm_handle* h, int rows, int cols, int mode) {
     return UGSM_OK;
 }
 
-// MGL:1033-1125 for one image (three channels).
-void build_pyramid(ugsm_handle* h, const uint8_t* d_rgb, size_t step, bool right) {
+// MGL:1033-1125 for `nimg` images (left [+ right]): 3*nimg planes per launch.
+void build_pyramid(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, size_t step) {
     const int levels = h->cfg.levels;
-    auto planes = [&](int i) { return right ? h->lv[i].R : h->lv[i].L; };
-    launch_unpack(h, d_rgb, step, h->lv[0].w, h->lv[0].h, planes(0), h->lv[0].pitch);
+    const int nimg = d_rgbR ? 2 : 1;
+    launch_unpack(h, d_rgbL, step, h->lv[0].w, h->lv[0].h, h->lv[0].L, h->lv[0].pitch);
+    if (d_rgbR) launch_unpack(h, d_rgbR, step, h->lv[0].w, h->lv[0].h, h->lv[0].R, h->lv[0].pitch);
+    auto planes = [&](int i, const float** out) {
+        for (int k = 0; k < 3; k++) {
+            out[k] = h->lv[i].L[k];
+            out[3 + k] = h->lv[i].R[k];
+        }
+    };
     for (int i = 0; i < levels; i++) {
         const LevelBuf& s = h->lv[i];
-        for (int k = 0; k < 3; k++) {
-            if (i == 0 && levels > 1)
-                launch_blur_decimate(h, 0, planes(0)[k], s.w, s.h, s.pitch, planes(1)[k], h->lv[1].w, h->lv[1].h,
-                                     h->lv[1].pitch);
-            if (i + 2 < levels)
-                launch_blur_decimate(h, 1, planes(i)[k], s.w, s.h, s.pitch, planes(i + 2)[k], h->lv[i + 2].w,
-                                     h->lv[i + 2].h, h->lv[i + 2].pitch);
+        const float* src[6];
+        const float* dstc[6];
+        planes(i, src);
+        if (i == 0 && levels > 1) {
+            planes(1, dstc);
+            launch_blur_decimate(h, 0, src, (float* const*)dstc, 3 * nimg, s.w, s.h, s.pitch, h->lv[1].w, h->lv[1].h,
+                                 h->lv[1].pitch);
+        }
+        if (i + 2 < levels) {
+            planes(i + 2, dstc);
+            launch_blur_decimate(h, 1, src, (float* const*)dstc, 3 * nimg, s.w, s.h, s.pitch, h->lv[i + 2].w,
+                                 h->lv[i + 2].h, h->lv[i + 2].pitch);
         }
     }
 }
@@ -384,7 +426,7 @@ void prepare_levels(ugsm_handle* h) {
                 h->launches += 2;
             }
         }
-        for (int k = 0; k < 3; k++) launch_energy(h, b.Lm[k], b.mw, b.mh, b.mpitch, b.U[k]);
+        launch_energy(h, b.Lm, b.U, 3, b.mw, b.mh, b.mpitch);
     }
 }
 
@@ -470,8 +512,7 @@ int run_pair(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int r
     h->launches = 0;
     h->kev_used = 0;
     CK(cudaEventRecord(h->ev[0], h->stream));
-    build_pyramid(h, d_rgbL, step, false);
-    build_pyramid(h, d_rgbR, step, true);
+    build_pyramid(h, d_rgbL, d_rgbR, step);
     prepare_levels(h);
     CK(cudaEventRecord(h->ev[1], h->stream));
     rc = run_levels(h);
@@ -805,7 +846,7 @@ int ugsm_stage_pyramid(ugsm_handle* h, const uint8_t* rgb, int rows, int cols, s
     rc = ensure_staging(h, step * (size_t)rows, 1);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->d_rgb[0], rgb, step * (size_t)rows, cudaMemcpyHostToDevice, h->stream));
-    build_pyramid(h, h->d_rgb[0], step, false);
+    build_pyramid(h, h->d_rgb[0], nullptr, step);
     CK(cudaGetLastError());
     for (int l = 0; l < h->cfg.levels; l++) {
         if (!out3[l]) continue;
@@ -851,8 +892,8 @@ int ugsm_stage_correlate(ugsm_handle* h, const float* L3, const float* R3, const
     CK(up2d(d[10], pitch, V, width, height, h->stream));
     CK(up2d(d[11], pitch, C, width, height, h->stream));
     K1Params p;
+    launch_energy(h, d, d + 6, 3, width, height, pitch);
     for (int k = 0; k < 3; k++) {
-        launch_energy(h, d[k], width, height, pitch, d[6 + k]);
         p.L[k] = d[k];
         p.R[k] = d[3 + k];
         p.U[k] = d[6 + k];
@@ -955,7 +996,7 @@ int ugsm_stage_match_level(ugsm_handle* h, const float* L3, const float* R3, flo
         CK(up2d(d[3 + k], pitch, R3 + k * n, width, height, h->stream));
         CK(up2d(d[9 + k], pitch, io[k], width, height, h->stream));
     }
-    for (int k = 0; k < 3; k++) launch_energy(h, d[k], width, height, pitch, d[6 + k]);
+    launch_energy(h, d, d + 6, 3, width, height, pitch);
     run_level(h, d, d + 3, d + 6, d + 9, d + 12, width, height, pitch, iters, passes, coarsest != 0);
     CK(cudaGetLastError());
     for (int k = 0; k < 3; k++) CK(down2d(io[k], d[9 + k], pitch, width, height, h->stream));
@@ -994,8 +1035,8 @@ int ugsm_bench_correlate(ugsm_handle* h, int width, int height, int reps, float*
     k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[10], np, -1.f, 1.f, 102u);
     k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[11], np, 0.3f, 1.f, 103u);
     K1Params p;
+    launch_energy(h, d, d + 6, 3, width, height, pitch);
     for (int k = 0; k < 3; k++) {
-        launch_energy(h, d[k], width, height, pitch, d[6 + k]);
         p.L[k] = d[k];
         p.R[k] = d[3 + k];
         p.U[k] = d[6 + k];
@@ -1027,6 +1068,29 @@ int ugsm_bench_correlate(ugsm_handle* h, int width, int height, int reps, float*
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     CK(cudaGetLastError());
+    *avg_ms = ms / reps;
+    return UGSM_OK;
+}
+
+__global__ void k_null(int) {}
+
+/* Launch floor: average time of `reps` back-to-back empty launches on the handle's stream. */
+int ugsm_bench_null(ugsm_handle* h, int reps, float* avg_ms) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (reps < 1 || !avg_ms) return fail(h, UGSM_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    for (int i = 0; i < 10; i++) k_null<<<1, 32, 0, h->stream>>>(i);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, h->stream));
+    for (int i = 0; i < reps; i++) k_null<<<1, 32, 0, h->stream>>>(i);
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     *avg_ms = ms / reps;
     return UGSM_OK;
 }
