@@ -215,7 +215,7 @@ void launch_k1(ugsm_handle* h, const K1Params& p) {
         k1_correlate<4, K1_TH><<<grid, 128, sizeof(K1Smem<4, K1_TH>), h->stream>>>(p);
     } else {
         dim3 grid(div_up(p.w, 30), div_up(p.h, K1S_TH));
-        k1_correlate_small<K1S_TH><<<grid, 96, 0, h->stream>>>(p);
+        k1_correlate_small<K1S_TH><<<grid, 256, 0, h->stream>>>(p);
     }
     h->launches++;
 }
