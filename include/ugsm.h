@@ -76,11 +76,11 @@ typedef struct ugsm_dims {
 /* Device-side timing of the last match call (CUDA events on the handle's stream). */
 typedef struct ugsm_timing {
     float total_ms;      /* whole device-resident pair (pyramid .. final planes) */
-    float pyramid_ms;    /* unpack + pyramid of both images */
-    float levels_ms;     /* coarse-to-fine loop */
+    float pyramid_ms;    /* unpack + pyramid of both images (0 when replayed from a graph) */
+    float levels_ms;     /* coarse-to-fine loop (0 when replayed from a graph) */
     float h2d_ms, d2h_ms;
     int32_t launches;    /* kernels launched by the last call */
-    float level_ms[UGSM_MAX_LEVELS];
+    float level_ms[UGSM_MAX_LEVELS]; /* with use_graph only level 0 is outside the graph and timed */
     /* Sum of the K1 (correlate) / K2 (smooth) launch durations per level, from CUDA events
      * recorded around every launch on the handle's stream; measured on the UGSM_TIMED_LEVELS
      * finest levels only (the others stay 0 so that events never pace the tiny kernels). */

@@ -81,6 +81,9 @@ struct ugsm_handle {
     int launches = 0;
     bool k_attr_set = false;
     int k1_nw = 2;
+    // CUDA graph of the per-pair launch sequence (pyramid levels .. last level), valid for the current shape
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_launches = 0;
 };
 
 namespace {
@@ -313,6 +316,8 @@ void launch_copy3(ugsm_handle* h, const float* s0, const float* s1, const float*
 
 // ------------------------------------------------------------------ per-shape buffers
 void release_shape(ugsm_handle* h) {
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
     if (h->arena) cudaFree(h->arena);
     h->arena = nullptr;
     h->arena_bytes = 0;
@@ -384,11 +389,13 @@ int prepare_shape(ugsm_handle* h, int rows, int cols, int mode) {
 }
 
 // MGL:1033-1125 for `nimg` images (left [+ right]): 3*nimg planes per launch.
-void build_pyramid(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, size_t step) {
-    const int levels = h->cfg.levels;
-    const int nimg = d_rgbR ? 2 : 1;
+void unpack_images(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, size_t step) {
     launch_unpack(h, d_rgbL, step, h->lv[0].w, h->lv[0].h, h->lv[0].L, h->lv[0].pitch);
     if (d_rgbR) launch_unpack(h, d_rgbR, step, h->lv[0].w, h->lv[0].h, h->lv[0].R, h->lv[0].pitch);
+}
+
+void build_pyramid(ugsm_handle* h, int nimg) {
+    const int levels = h->cfg.levels;
     auto planes = [&](int i, const float** out) {
         for (int k = 0; k < 3; k++) {
             out[k] = h->lv[i].L[k];
@@ -472,11 +479,12 @@ void run_level(ugsm_handle* h, float* const L[3], float* const R[3], float* cons
     }
 }
 
-// MGL:1196-1318 coarse-to-fine loop.
-int run_levels(ugsm_handle* h) {
+// MGL:1196-1318 coarse-to-fine loop over levels [hi .. lo].  `events` = record the per-level and
+// per-launch timing events (not possible while capturing a graph: those cannot be timed).
+int run_levels(ugsm_handle* h, int hi, int lo, bool events) {
     const int levels = h->cfg.levels;
     const int fl = h->cfg.fovea_level;
-    for (int i = levels - 1; i >= 0; i--) {
+    for (int i = hi; i >= lo; i--) {
         LevelBuf& b = h->lv[i];
         if (i == levels - 1) {
             // zero start (the reference reads uninitialised malloc here, MGL:1247)
@@ -493,8 +501,8 @@ int run_levels(ugsm_handle* h) {
             }
         }
         run_level(h, b.Lm, b.Rm, b.U, b.st, h->tmp, b.mw, b.mh, b.mpitch, b.iters, b.smooth, i == levels - 1,
-                  i < UGSM_TIMED_LEVELS ? i : -1);
-        CK(cudaEventRecord(h->ev[4 + i], h->stream));
+                  (events && i < UGSM_TIMED_LEVELS) ? i : -1);
+        if (events) CK(cudaEventRecord(h->ev[4 + i], h->stream));
     }
     return UGSM_OK;
 }
@@ -512,11 +520,46 @@ int run_pair(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int r
     h->launches = 0;
     h->kev_used = 0;
     CK(cudaEventRecord(h->ev[0], h->stream));
-    build_pyramid(h, d_rgbL, d_rgbR, step);
-    prepare_levels(h);
-    CK(cudaEventRecord(h->ev[1], h->stream));
-    rc = run_levels(h);
-    if (rc) return rc;
+    unpack_images(h, d_rgbL, d_rgbR, step);  // reads the caller's buffers: stays outside the graph
+    const int levels = h->cfg.levels;
+    if (!h->cfg.use_graph || levels < 2) {
+        build_pyramid(h, 2);
+        prepare_levels(h);
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        rc = run_levels(h, levels - 1, 0, true);
+        if (rc) return rc;
+    } else {
+        // Graph: pyramid + crops/energy + levels [levels-1 .. 1] (hundreds of short launches, where the
+        // ~4 us launch floor matters).  Level 0 (ms-long kernels) stays outside so that its K1/K2
+        // launches keep their timing events.
+        if (!h->graph_exec) {
+            // Capture once per shape: every buffer the sequence touches belongs to the handle's arena.
+            const int l0 = h->launches;
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+            build_pyramid(h, 2);
+            prepare_levels(h);
+            rc = run_levels(h, levels - 1, 1, false);
+            cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+            if (rc || e != cudaSuccess || !g) {
+                if (g) cudaGraphDestroy(g);
+                return rc ? rc : fail(h, UGSM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+            }
+            e = cudaGraphInstantiate(&h->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) {
+                h->graph_exec = nullptr;
+                return fail(h, UGSM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+            }
+            h->graph_launches = h->launches - l0;
+            h->launches = l0;
+        }
+        CK(cudaGraphLaunch(h->graph_exec, h->stream));
+        h->launches += h->graph_launches;
+        CK(cudaEventRecord(h->ev[4 + 1], h->stream));
+        rc = run_levels(h, 0, 0, true);
+        if (rc) return rc;
+    }
     CK(cudaEventRecord(h->ev[2], h->stream));
     CK(cudaGetLastError());
     return UGSM_OK;
@@ -528,23 +571,28 @@ int finish_timing(ugsm_handle* h) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]));
     t.total_ms = ms;
-    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-    t.pyramid_ms = ms;
-    CK(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]));
-    t.levels_ms = ms;
-    const int levels = h->cfg.levels;
-    for (int i = levels - 1; i >= 0; i--) {
-        cudaEvent_t prev = (i == levels - 1) ? h->ev[1] : h->ev[4 + i + 1];
-        CK(cudaEventElapsedTime(&ms, prev, h->ev[4 + i]));
-        t.level_ms[i] = ms;
-    }
     t.launches = h->launches;
-    for (int i = 0; i < UGSM_MAX_LEVELS; i++) t.k1_ms[i] = t.k2_ms[i] = 0.f;
+    t.pyramid_ms = t.levels_ms = 0.f;
+    for (int i = 0; i < UGSM_MAX_LEVELS; i++) t.level_ms[i] = t.k1_ms[i] = t.k2_ms[i] = 0.f;
+    const int levels = h->cfg.levels;
+    const bool graph = h->cfg.use_graph && levels >= 2;  // then only level 0 has inner events
+    float v = 0;
+    if (!graph) {
+        CK(cudaEventElapsedTime(&v, h->ev[0], h->ev[1]));
+        t.pyramid_ms = v;
+        CK(cudaEventElapsedTime(&v, h->ev[1], h->ev[2]));
+        t.levels_ms = v;
+    }
+    for (int i = graph ? 0 : levels - 1; i >= 0; i--) {
+        cudaEvent_t prev = (i == levels - 1) ? h->ev[1] : h->ev[4 + i + 1];
+        CK(cudaEventElapsedTime(&v, prev, h->ev[4 + i]));
+        t.level_ms[i] = v;
+    }
     for (int s = 0; s < h->kev_used; s++) {
-        CK(cudaEventElapsedTime(&ms, h->kev[3 * s], h->kev[3 * s + 1]));
-        t.k1_ms[h->kev_level[s]] += ms;
-        CK(cudaEventElapsedTime(&ms, h->kev[3 * s + 1], h->kev[3 * s + 2]));
-        t.k2_ms[h->kev_level[s]] += ms;
+        CK(cudaEventElapsedTime(&v, h->kev[3 * s], h->kev[3 * s + 1]));
+        t.k1_ms[h->kev_level[s]] += v;
+        CK(cudaEventElapsedTime(&v, h->kev[3 * s + 1], h->kev[3 * s + 2]));
+        t.k2_ms[h->kev_level[s]] += v;
     }
     return UGSM_OK;
 }
@@ -627,7 +675,7 @@ void ugsm_config_default(ugsm_config* cfg) {
     cfg->smooth_passes = 5;
     cfg->smooth_passes_fine = 10;
     cfg->max_iters = 0;
-    cfg->use_graph = 0;
+    cfg->use_graph = 1;
 }
 
 int ugsm_query_dims(const ugsm_config* cfg, int rows, int cols, int mode, ugsm_dims* out) {
@@ -846,7 +894,8 @@ int ugsm_stage_pyramid(ugsm_handle* h, const uint8_t* rgb, int rows, int cols, s
     rc = ensure_staging(h, step * (size_t)rows, 1);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->d_rgb[0], rgb, step * (size_t)rows, cudaMemcpyHostToDevice, h->stream));
-    build_pyramid(h, h->d_rgb[0], nullptr, step);
+    unpack_images(h, h->d_rgb[0], nullptr, step);
+    build_pyramid(h, 1);
     CK(cudaGetLastError());
     for (int l = 0; l < h->cfg.levels; l++) {
         if (!out3[l]) continue;
