@@ -1,5 +1,5 @@
 import os, sys, time
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import numpy as np
 from ug_stereomatcher_b200 import capi, synth
 h = capi.Handle()

@@ -1,5 +1,5 @@
 import sys
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from ug_stereomatcher_b200 import capi
 h = capi.Handle()
 w, hh = 4928, 3264

@@ -1,5 +1,5 @@
 import sys, time, threading
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import numpy as np, torch
 from ug_stereomatcher_b200 import capi, synth
 L, R, _, _ = synth.make_pair(4928, 3264, 0)
