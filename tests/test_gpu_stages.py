@@ -144,3 +144,53 @@ def test_match_level_bit_exact_vs_live_reference_cuda(gpu, tmp_path):
         got = gpu.stage_match_level(L3, R3, h0, v0, c0, iters, passes, coarsest)
         for g, r, n in zip(got, ref, "HVC"):
             _assert_same(g, r, "%s %s vs live reference CUDA" % (name, n))
+
+
+def _assert_same_away_from_nonfinite(g, w, what):
+    """Bit equality everywhere except within 2 px of a non-finite value: the oracle multiplies the box
+    filter's zero outer taps (0 * NaN = NaN, MatchLib.cu:1616-1623), the CUDA kernel skips them.  State
+    planes are never non-finite in the matcher; this only isolates the division."""
+    bad = ~np.isfinite(w) | ~np.isfinite(g)
+    near = bad.copy()
+    for d in (1, 2):
+        near[d:, :] |= bad[:-d, :]
+        near[:-d, :] |= bad[d:, :]
+        near[:, d:] |= bad[:, :-d]
+        near[:, :-d] |= bad[:, d:]
+    ok = (g == w) | near
+    assert ok.all(), "%s: %d px differ away from non-finite values" % (what, int((~ok).sum()))
+    assert (~near).mean() > 0.5, what
+
+
+def test_smooth_special_values_bit_exact(gpu, oracle):
+    """The smoothing divisions use a guarded fast path with a shared reciprocal; zeros, denormals, values
+    outside [2^-62, 2^62] and zero denominators must take the full IEEE path and still match the oracle."""
+    rng = np.random.default_rng(99)
+    rows, cols = 70, 150
+    H, V, C = _state(rng, rows, cols)
+    specials = np.array([0.0, -0.0, 1e-45, -1e-42, 1e-38, 3e-30, -7e-25, 1e-20, 1e19, -3e25, 2.0 ** -62, 2.0 ** 62,
+                         2.0 ** -63, 2.0 ** 63], np.float32)
+    for plane in (H, V):
+        ys = rng.integers(0, rows, 400)
+        xs = rng.integers(0, cols, 400)
+        plane[ys, xs] = specials[rng.integers(0, len(specials), 400)]
+    H[10:20, 30:60] = 0.0          # zero numerators (the coarsest level starts like this)
+    C[40:44, 100:120] = 0.0        # zero denominators -> 0/0 and x/0
+    C[50:52, 10:30] = 1e-30        # tiny denominators
+    C[5:7, 5:40] = 3e20            # huge denominators
+    for passes in (1, 5):
+        got = gpu.stage_smooth(H, V, C, passes)
+        want = oracle.smooth(H, V, C, passes)
+        for g, w, n in zip(got, want, "HVC"):
+            _assert_same_away_from_nonfinite(g, w, "smooth specials %s S=%d" % (n, passes))
+    # same through the small-level kernel (16x16 tiles, one thread per cell) and the big one
+    for shape in ((40, 60), (700, 1100)):
+        H2, V2, C2 = _state(rng, *shape)
+        ys = rng.integers(0, shape[0], 300)
+        xs = rng.integers(0, shape[1], 300)
+        H2[ys, xs] = specials[rng.integers(0, len(specials), 300)]
+        C2[ys[:50], xs[:50]] = 0.0
+        got = gpu.stage_smooth(H2, V2, C2, 5)
+        want = oracle.smooth(H2, V2, C2, 5)
+        for g, w, n in zip(got, want, "HVC"):
+            _assert_same_away_from_nonfinite(g, w, "smooth specials %s %s" % (n, shape))
