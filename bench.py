@@ -280,7 +280,11 @@ def run_gpu(args):
     # ---- B. end to end through the host-buffer C-ABI call (pinned host buffers), NF in flight ----
     e2e_ms_step, _, _ = region(host_step, NF, args.steps)
     # ---- C. one pair in flight: latency per pair and the clean per-launch K1 timing (roofline) ----
+    # (bracketed by cudaProfilerStart/Stop so that `ncu --profile-from-start off` instruments exactly this
+    # region: one launch list per pair without slowing the other ~10k launches of the run down)
+    torch.cuda.profiler.start()
     lat_ms, _, k1_sum = region(dev_step, 1, args.steps)
+    torch.cuda.profiler.stop()
     k1_avg = k1_sum / (2 * args.steps)  # level 0 runs 2 iterations (MatchGPULib.cpp:1741)
     last = handles[0].timing()
     e2e_lat_ms, _, _ = region(host_step, 1, max(3, args.steps // 2))

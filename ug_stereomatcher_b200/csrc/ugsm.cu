@@ -709,6 +709,7 @@ int ugsm_create(const ugsm_config* cfg, ugsm_handle** out) {
     if (prop.major != 10)
         return fail(nullptr, UGSM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
                     prop.major, prop.minor);
+    if (const char* e = getenv("UGSM_USE_GRAPH")) c.use_graph = atoi(e) ? 1 : 0;  // override for profiling runs
     h = new ugsm_handle();
     h->cfg = c;
     h->device = dev;
