@@ -168,6 +168,34 @@ int ugsm_bench_smooth(ugsm_handle* h, int width, int height, int passes, int rep
 /* Launch floor of the stream: average time of `reps` back-to-back empty kernel launches. */
 int ugsm_bench_null(ugsm_handle* h, int reps, float* avg_ms);
 
+/* ---- row-band execution of the finest levels across GPUs ------------------------
+ * One process per GPU, every rank holds the whole pyramid (levels >= split_levels are computed
+ * replicated); for the levels below split_levels each rank runs K1/K2 only on its band of rows and
+ * the caller exchanges halo rows of (H,V,C) between iterations (NVLink P2P / NCCL; see
+ * ug_stereomatcher_b200/rowband.py).  All calls enqueue on the handle's stream and do not
+ * synchronise; buffers are device pointers. */
+typedef struct ugsm_band_level {
+    int32_t width, height, pitch; /* level dims, pitch in floats */
+    int32_t iters, smooth;        /* iterations and smoothing passes of this level */
+    float* state[3];              /* H, V, C planes of the level (pitched), the ones halos are exchanged on */
+} ugsm_band_level;
+
+/* Pyramid of both images + levels [levels-1 .. split_levels] + upsample into level split_levels-1. */
+int ugsm_band_begin(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int rows, int cols, size_t step,
+                    int split_levels);
+int ugsm_band_level_info(ugsm_handle* h, int level, ugsm_band_level* out);
+/* Iteration m (1-based) of `level` for rows [y_begin, y_end): K1 on the band extended by `ext` rows
+ * (clipped to the image; ext >= smooth+1 so that K2 needs no exchange of K1's output), then K2. */
+int ugsm_band_iteration(ugsm_handle* h, int level, int m, int y_begin, int y_end, int ext);
+/* Upsample rows [y_begin, y_end) of level-1 from `level` (K3). */
+int ugsm_band_upsample(ugsm_handle* h, int level, int y_begin, int y_end);
+/* Halo staging: copy rows [y_begin, y_end) of the level's H, V, C planes into / out of one contiguous
+ * device buffer of 3 * (y_end - y_begin) * pitch floats (plane-major). */
+int ugsm_band_pack(ugsm_handle* h, int level, int y_begin, int y_end, float* d_buf);
+int ugsm_band_unpack(ugsm_handle* h, int level, int y_begin, int y_end, const float* d_buf);
+/* Copy rows [y_begin, y_end) of the level-0 result into dense (pitch == width) output planes. */
+int ugsm_band_emit(ugsm_handle* h, float* dH, float* dV, float* dC, int y_begin, int y_end);
+
 const char* ugsm_version(void);
 
 #ifdef __cplusplus

@@ -22,7 +22,9 @@ SYMBOLS = [
     "ugsm_match_full", "ugsm_match_foveated", "ugsm_match_full_device", "ugsm_match_foveated_device",
     "ugsm_get_fovea_images", "ugsm_get_pyramid_level", "ugsm_get_level_disparity", "ugsm_get_timing",
     "ugsm_stage_pyramid", "ugsm_stage_correlate", "ugsm_stage_smooth", "ugsm_stage_upsample",
-    "ugsm_stage_match_level", "ugsm_bench_correlate", "ugsm_bench_smooth", "ugsm_bench_null", "ugsm_version",
+    "ugsm_stage_match_level", "ugsm_bench_correlate", "ugsm_bench_smooth", "ugsm_bench_null", "ugsm_version", "ugsm_band_begin",
+    "ugsm_band_level_info", "ugsm_band_iteration", "ugsm_band_upsample", "ugsm_band_emit", "ugsm_band_pack",
+    "ugsm_band_unpack",
 ]
 
 
@@ -66,6 +68,17 @@ class Timing(C.Structure):
         ("level_ms", C.c_float * MAX_LEVELS),
         ("k1_ms", C.c_float * MAX_LEVELS),
         ("k2_ms", C.c_float * MAX_LEVELS),
+    ]
+
+
+class BandLevel(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("pitch", C.c_int32),
+        ("iters", C.c_int32),
+        ("smooth", C.c_int32),
+        ("state", C.c_void_p * 3),
     ]
 
 
@@ -115,6 +128,13 @@ def lib():
         L.ugsm_bench_correlate.argtypes = [vp, i, i, i, C.POINTER(C.c_float)]
         L.ugsm_bench_smooth.argtypes = [vp, i, i, i, i, C.POINTER(C.c_float)]
         L.ugsm_bench_null.argtypes = [vp, i, C.POINTER(C.c_float)]
+        L.ugsm_band_begin.argtypes = [vp, vp, vp, i, i, sz, i]
+        L.ugsm_band_level_info.argtypes = [vp, i, C.POINTER(BandLevel)]
+        L.ugsm_band_iteration.argtypes = [vp, i, i, i, i, i]
+        L.ugsm_band_upsample.argtypes = [vp, i, i, i]
+        L.ugsm_band_emit.argtypes = [vp, vp, vp, vp, i, i]
+        L.ugsm_band_pack.argtypes = [vp, i, i, i, vp]
+        L.ugsm_band_unpack.argtypes = [vp, i, i, i, vp]
         _LIB = L
     return _LIB
 
@@ -177,7 +197,9 @@ class Handle:
             raise UgsmError(rc, lib().ugsm_last_error(self._h).decode())
 
     def set_stream(self, cuda_stream_ptr):
-        self._ck(lib().ugsm_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+        """cudaStream_t as an integer.  0 / None restores the handle's own stream (torch's default stream
+        has handle 0: pass an explicit torch.cuda.Stream when ordering against other work matters)."""
+        self._ck(lib().ugsm_set_stream(self._h, C.c_void_p(cuda_stream_ptr or None)))
 
     def timing(self):
         t = Timing()
@@ -289,6 +311,30 @@ class Handle:
         self._ck(lib().ugsm_stage_match_level(self._h, _p(L3), _p(R3), _p(H), _p(V), _p(Cc), w, h, iters, passes,
                                               int(coarsest)))
         return H, V, Cc
+
+    # -- row-band execution (device pointers; enqueue only, no synchronisation) -----------------
+    def band_begin(self, d_rgbL, d_rgbR, rows, cols, step, split_levels):
+        self._ck(lib().ugsm_band_begin(self._h, d_rgbL, d_rgbR, rows, cols, step, split_levels))
+
+    def band_level_info(self, level):
+        b = BandLevel()
+        self._ck(lib().ugsm_band_level_info(self._h, level, C.byref(b)))
+        return b
+
+    def band_iteration(self, level, m, y_begin, y_end, ext):
+        self._ck(lib().ugsm_band_iteration(self._h, level, m, y_begin, y_end, ext))
+
+    def band_upsample(self, level, y_begin, y_end):
+        self._ck(lib().ugsm_band_upsample(self._h, level, y_begin, y_end))
+
+    def band_pack(self, level, y_begin, y_end, d_buf):
+        self._ck(lib().ugsm_band_pack(self._h, level, y_begin, y_end, d_buf))
+
+    def band_unpack(self, level, y_begin, y_end, d_buf):
+        self._ck(lib().ugsm_band_unpack(self._h, level, y_begin, y_end, d_buf))
+
+    def band_emit(self, dH, dV, dC, y_begin, y_end):
+        self._ck(lib().ugsm_band_emit(self._h, dH, dV, dC, y_begin, y_end))
 
     def bench_correlate(self, width, height, reps=10):
         ms = C.c_float()

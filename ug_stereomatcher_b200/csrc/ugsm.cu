@@ -210,11 +210,13 @@ void launch_k1(ugsm_handle* h, const K1Params& p) {
     // Large levels: 4-warp CTAs (120 columns x 16 rows), channels in sequence.  Small levels:
     // 30 x 8 tiles with one warp per colour channel, so that the few tiles there spread over
     // more SMs and the dependent chain per launch is short.
-    if ((long)p.w * p.h >= K1_SMALL_PIXELS && h->k1_nw == 2) {
-        dim3 grid(div_up(p.w, 60), div_up(p.h, K1_TH));
+    const int band_rows = p.y_end - p.y_begin;
+    const bool big = (long)p.w * p.h >= K1_SMALL_PIXELS || band_rows != p.h;  // a row band always uses the band-aware kernel
+    if (big && h->k1_nw == 2) {
+        dim3 grid(div_up(p.w, 60), div_up(band_rows, K1_TH));
         k1_correlate<2, K1_TH><<<grid, 64, sizeof(K1Smem<2, K1_TH>), h->stream>>>(p);
-    } else if ((long)p.w * p.h >= K1_SMALL_PIXELS) {
-        dim3 grid(div_up(p.w, 120), div_up(p.h, K1_TH));
+    } else if (big) {
+        dim3 grid(div_up(p.w, 120), div_up(band_rows, K1_TH));
         k1_correlate<4, K1_TH><<<grid, 128, sizeof(K1Smem<4, K1_TH>), h->stream>>>(p);
     } else {
         dim3 grid(div_up(p.w, 30), div_up(p.h, K1S_TH));
@@ -224,8 +226,12 @@ void launch_k1(ugsm_handle* h, const K1Params& p) {
 }
 
 void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci, float* Ho, float* Vo, float* Co,
-               int w, int hh, int pitch, int passes) {
+               int w, int hh, int pitch, int passes, int y_begin = 0, int y_end = -1) {
+    if (y_end < 0) y_end = hh;
+    const bool banded = (y_begin != 0 || y_end != hh);
     K2Params p;
+    p.y_begin = y_begin;
+    p.y_end = y_end;
     p.Hi = Hi;
     p.Vi = Vi;
     p.Ci = Ci;
@@ -238,7 +244,7 @@ void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci
     p.passes = passes;
     p.a1 = h->taps.a[1];
     const int R = passes + 1;
-    if ((long)w * hh < K2_SMALL_PIXELS && K2S_T + 2 * R <= 32) {
+    if (!banded && (long)w * hh < K2_SMALL_PIXELS && K2S_T + 2 * R <= 32) {
         // small levels: 16x16 tiles, one thread per region cell (latency-oriented)
         p.th = K2S_T;
         p.hpad = R;
@@ -254,19 +260,21 @@ void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci
     // small levels so that there are at least ~2 CTAs per SM.
     int th = K2_MAX_BH - 2 * R;
     const int cols = div_up(w, twu);
-    while (th > 8 && (long)cols * div_up(hh, th) < 2L * h->sm_count) th = (th + 1) / 2;
-    if (th > hh) th = hh;
+    const int brows = y_end - y_begin;
+    while (th > 8 && (long)cols * div_up(brows, th) < 2L * h->sm_count) th = (th + 1) / 2;
+    if (th > brows) th = brows;
     p.th = th;
-    dim3 grid(cols, div_up(hh, th));
+    dim3 grid(cols, div_up(brows, th));
     k2_smooth_box<<<grid, K2_NWARP * 32, k2_smem_bytes(th + 2 * R), h->stream>>>(p);
     h->launches++;
 }
 
 void launch_k3(ugsm_handle* h, float* const src[3], int w, int hh, int spitch, int crop_x, int crop_y,
-               float* const dst[3], int ow, int oh, int dpitch) {
-    dim3 block(32, 8), grid(div_up(ow, 32), div_up(oh, 8));
+               float* const dst[3], int ow, int oh, int dpitch, int oy_begin = 0, int oy_end = -1) {
+    if (oy_end < 0) oy_end = oh;
+    dim3 block(32, 8), grid(div_up(ow, 32), div_up(oy_end - oy_begin, 8));
     k3_upsample<<<grid, block, 0, h->stream>>>(src[0], src[1], src[2], w, hh, spitch, crop_x, crop_y, dst[0], dst[1],
-                                               dst[2], ow, oh, dpitch);
+                                               dst[2], ow, oy_end, dpitch, oy_begin);
     h->launches++;
 }
 
@@ -464,6 +472,8 @@ void run_level(ugsm_handle* h, float* const L[3], float* const R[3], float* cons
         p.w = w;
         p.h = hh;
         p.pitch = pitch;
+        p.y_begin = 0;
+        p.y_end = hh;
         p.T = T;
         p.first_coarsest = (coarsest && m == 1) ? 1 : 0;
         p.dbg_srcx = nullptr;
@@ -957,6 +967,8 @@ int ugsm_stage_correlate(ugsm_handle* h, const float* L3, const float* R3, const
     p.w = width;
     p.h = height;
     p.pitch = pitch;
+    p.y_begin = 0;
+    p.y_end = height;
     p.T = threshold;
     p.first_coarsest = first_coarsest ? 1 : 0;
     p.dbg_srcx = dsx;
@@ -1054,6 +1066,134 @@ int ugsm_stage_match_level(ugsm_handle* h, const float* L3, const float* R3, flo
     return UGSM_OK;
 }
 
+// ------------------------------------------------------------------- row-band execution
+int ugsm_band_begin(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int rows, int cols, size_t step,
+                    int split_levels) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!d_rgbL || !d_rgbR || step < (size_t)cols * 3) return fail(h, UGSM_ERR_INVALID, "bad argument");
+    const int levels = h->cfg.levels;
+    if (split_levels < 1 || split_levels >= levels) return fail(h, UGSM_ERR_INVALID, "split_levels out of range");
+    CK(cudaSetDevice(h->device));
+    int rc = set_kernel_attrs(h);
+    if (rc) return rc;
+    rc = prepare_shape(h, rows, cols, 0);
+    if (rc) return rc;
+    h->launches = 0;
+    h->kev_used = 0;
+    unpack_images(h, d_rgbL, d_rgbR, step);
+    build_pyramid(h, 2);
+    prepare_levels(h);
+    rc = run_levels(h, levels - 1, split_levels, false);
+    if (rc) return rc;
+    LevelBuf& c = h->lv[split_levels];
+    LevelBuf& b = h->lv[split_levels - 1];
+    launch_k3(h, c.st, c.mw, c.mh, c.mpitch, 0, 0, b.st, b.mw, b.mh, b.mpitch);
+    CK(cudaGetLastError());
+    return UGSM_OK;
+}
+
+int ugsm_band_level_info(ugsm_handle* h, int level, ugsm_band_level* out) {
+    if (!h || !out) return UGSM_ERR_INVALID;
+    if (h->lv.empty() || level < 0 || level >= (int)h->lv.size()) return fail(h, UGSM_ERR_INVALID, "no such level");
+    LevelBuf& b = h->lv[level];
+    out->width = b.mw;
+    out->height = b.mh;
+    out->pitch = b.mpitch;
+    out->iters = b.iters;
+    out->smooth = b.smooth;
+    for (int k = 0; k < 3; k++) out->state[k] = b.st[k];
+    return UGSM_OK;
+}
+
+int ugsm_band_iteration(ugsm_handle* h, int level, int m, int y_begin, int y_end, int ext) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (h->lv.empty() || level < 0 || level >= (int)h->lv.size()) return fail(h, UGSM_ERR_INVALID, "no such level");
+    LevelBuf& b = h->lv[level];
+    if (m < 1 || m > b.iters || y_begin < 0 || y_end > b.mh || y_begin >= y_end || ext < b.smooth + 1)
+        return fail(h, UGSM_ERR_INVALID, "bad band iteration arguments");
+    CK(cudaSetDevice(h->device));
+    float T = 1.0f;  // MGL:1673, replayed up to iteration m
+    for (int k = 1; k < m; k++) T = threshold_after(b.iters, k, T);
+    K1Params p;
+    for (int k = 0; k < 3; k++) {
+        p.L[k] = b.Lm[k];
+        p.R[k] = b.Rm[k];
+        p.U[k] = b.U[k];
+    }
+    p.H = b.st[0];
+    p.V = b.st[1];
+    p.C = b.st[2];
+    p.Hn = h->tmp[0];
+    p.Vn = h->tmp[1];
+    p.Cn = h->tmp[2];
+    p.w = b.mw;
+    p.h = b.mh;
+    p.pitch = b.mpitch;
+    p.y_begin = y_begin - ext < 0 ? 0 : y_begin - ext;
+    p.y_end = y_end + ext > b.mh ? b.mh : y_end + ext;
+    p.T = T;
+    p.first_coarsest = (level == h->cfg.levels - 1 && m == 1) ? 1 : 0;
+    p.dbg_srcx = p.dbg_srcy = nullptr;
+    p.dbg_bh = p.dbg_bv = nullptr;
+    p.tp = h->taps;
+    launch_k1(h, p);
+    launch_k2(h, h->tmp[0], h->tmp[1], h->tmp[2], b.st[0], b.st[1], b.st[2], b.mw, b.mh, b.mpitch, b.smooth, y_begin,
+              y_end);
+    CK(cudaGetLastError());
+    return UGSM_OK;
+}
+
+int ugsm_band_upsample(ugsm_handle* h, int level, int y_begin, int y_end) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (h->lv.empty() || level < 1 || level >= (int)h->lv.size()) return fail(h, UGSM_ERR_INVALID, "no such level");
+    LevelBuf& c = h->lv[level];
+    LevelBuf& b = h->lv[level - 1];
+    if (y_begin < 0) y_begin = 0;
+    if (y_end > b.mh) y_end = b.mh;
+    if (y_begin >= y_end) return fail(h, UGSM_ERR_INVALID, "empty row range");
+    CK(cudaSetDevice(h->device));
+    launch_k3(h, c.st, c.mw, c.mh, c.mpitch, 0, 0, b.st, b.mw, b.mh, b.mpitch, y_begin, y_end);
+    CK(cudaGetLastError());
+    return UGSM_OK;
+}
+
+static int band_copy(ugsm_handle* h, int level, int y_begin, int y_end, float* buf, bool pack) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (h->lv.empty() || level < 0 || level >= (int)h->lv.size() || !buf)
+        return fail(h, UGSM_ERR_INVALID, "bad argument");
+    LevelBuf& b = h->lv[level];
+    if (y_begin < 0 || y_end > b.mh || y_begin >= y_end) return fail(h, UGSM_ERR_INVALID, "bad row range");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)(y_end - y_begin) * b.mpitch;
+    for (int k = 0; k < 3; k++) {
+        float* plane = b.st[k] + (size_t)y_begin * b.mpitch;
+        if (pack)
+            CK(cudaMemcpyAsync(buf + k * n, plane, n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        else
+            CK(cudaMemcpyAsync(plane, buf + k * n, n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return UGSM_OK;
+}
+int ugsm_band_pack(ugsm_handle* h, int level, int y_begin, int y_end, float* d_buf) {
+    return band_copy(h, level, y_begin, y_end, d_buf, true);
+}
+int ugsm_band_unpack(ugsm_handle* h, int level, int y_begin, int y_end, const float* d_buf) {
+    return band_copy(h, level, y_begin, y_end, const_cast<float*>(d_buf), false);
+}
+
+int ugsm_band_emit(ugsm_handle* h, float* dH, float* dV, float* dC, int y_begin, int y_end) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (h->lv.empty() || !dH || !dV || !dC) return fail(h, UGSM_ERR_INVALID, "bad argument");
+    LevelBuf& b = h->lv[0];
+    if (y_begin < 0 || y_end > b.mh || y_begin >= y_end) return fail(h, UGSM_ERR_INVALID, "bad row range");
+    CK(cudaSetDevice(h->device));
+    const size_t so = (size_t)y_begin * b.mpitch, dd = (size_t)y_begin * b.mw;
+    launch_copy3(h, b.st[0] + so, b.st[1] + so, b.st[2] + so, b.mpitch, dH + dd, dV + dd, dC + dd, b.mw, b.mw,
+                 y_end - y_begin);
+    CK(cudaGetLastError());
+    return UGSM_OK;
+}
+
 // ------------------------------------------------------------------- micro-benchmarks
 __global__ void k_fill_synth(float* p, size_t n, float lo, float hi, uint32_t seed) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -1100,6 +1240,8 @@ int ugsm_bench_correlate(ugsm_handle* h, int width, int height, int reps, float*
     p.w = width;
     p.h = height;
     p.pitch = pitch;
+    p.y_begin = 0;
+    p.y_end = height;
     p.T = 1.0f;
     p.first_coarsest = 0;
     p.dbg_srcx = p.dbg_srcy = nullptr;
