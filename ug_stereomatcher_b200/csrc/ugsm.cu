@@ -189,7 +189,7 @@ constexpr int K1_TH = 16;
 constexpr int K1S_TH = 8;
 constexpr long K1_SMALL_PIXELS = 400000;  // levels below this use k1_correlate_small
 constexpr long K2_SMALL_PIXELS = 700000;  // levels below this use k2_smooth_box_small
-constexpr int K2_MAX_BH = 64;  // region rows (tile + 2 halos): 2*3*64*128*4 B = 192 KB of shared memory
+constexpr int K2_MAX_BH = 72;  // region rows (tile + 2 halos): 2*3*72*128*4 B = 216 KB of shared memory (227 KB max)
 
 size_t k2_smem_bytes(int bh) { return (size_t)2 * 3 * K2_BW * bh * sizeof(float); }
 
