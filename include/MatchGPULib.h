@@ -12,8 +12,8 @@
 // malloc'd [14][3] array of planes; the caller frees the first getFoveateLevel() levels
 // (UG_GPU_matcher.cpp:414-418); ugsmFreeStack() frees all of it.
 // Differences, all deliberate: no cudaDeviceReset() per pair (MatchGPULib.cpp:400), no global device
-// state, errors are reported (lastError(), NULL return) instead of exit(); match(..., fov = 1)
-// (hierarchicalDisparity, never called by the node) is not part of this path and returns NULL.
+// state, errors are reported (lastError(), NULL return) instead of exit().  match(..., fov = 1) runs the
+// foveated matcher and the hierarchicalDisparity composite (MatchGPULib.cpp:355-360, 2589-2701).
 #ifndef UGSM_MATCHGPULIB_H
 #define UGSM_MATCHGPULIB_H
 

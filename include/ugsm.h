@@ -119,6 +119,14 @@ int ugsm_match_full_device(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t*
 int ugsm_match_foveated_device(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int rows, int cols,
                                size_t step, float* d_stackH, float* d_stackV, float* d_stackC);
 
+/* Foveated match + hierarchical composite = MatchGPULib::match(L, R, fov = 1) (MatchGPULib.cpp:355-360,
+ * hierarchicalDisparity MatchGPULib.cpp:2589-2701): full-resolution H, V, C (rows*cols floats each) in which
+ * every level's fovea is pasted over the x sqrt2 upsampled composite of the coarser levels. */
+int ugsm_match_composite(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step,
+                         float* H, float* V, float* C);
+int ugsm_match_composite_device(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int rows, int cols,
+                                size_t step, float* dH, float* dV, float* dC);
+
 /* After a foveated match: copy the image foveas the reference exports through
  * leftFov/rightFov (MatchGPULib.cpp:644-647) -- level `level`, 3 planes of
  * match_width x match_height floats each, host buffers. */
@@ -156,6 +164,10 @@ int ugsm_stage_smooth(ugsm_handle* h, float* H, float* V, float* C, int width, i
 int ugsm_stage_upsample(ugsm_handle* h, const float* H, const float* V, const float* C, int width, int height,
                         int fine_w, int fine_h, int crop_x, int crop_y, int out_w, int out_h, float* Ho, float* Vo,
                         float* Co);
+
+/* K4 chain: hierarchicalDisparity on a given foveated stack (layout of ugsm_match_foveated). */
+int ugsm_stage_composite(ugsm_handle* h, const float* stackH, const float* stackV, const float* stackC, int rows,
+                         int cols, float* H, float* V, float* C);
 
 /* One whole level: `iters` iterations of K1+K2 with the reference threshold schedule. */
 int ugsm_stage_match_level(ugsm_handle* h, const float* L3, const float* R3, float* H, float* V, float* C, int width,

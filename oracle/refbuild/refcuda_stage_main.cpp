@@ -5,6 +5,7 @@
 //   refcuda_stage conv   W H in.f32(3 planes) out.f32                     -> MatchGPULib::convolutionGPU
 //   refcuda_stage decim  W H scale W2 H2 in.f32(3 planes) out.f32         -> MatchGPULib::subsampledimageGPU
 //   refcuda_stage updisp W H W2 H2 in.f32(3 planes) out.f32               -> MatchGPULib::subsampleDisp
+//   refcuda_stage hier   W H fl in.f32(stack: 3 x fl x fovH x fovW) out.f32 -> MatchGPULib::hierarchicalDisparity
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,8 +34,9 @@ static void wr(const char* path, float** planes, int np, size_t n) {
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
     std::string mode = argv[1];
-    char* fake_argv[] = {argv[0], nullptr};
-    MatchGPULib m(1, fake_argv);
+    char a1[] = "x";
+    char* fake_argv[] = {argv[0], a1, (mode == "hier" && argc > 4) ? argv[4] : nullptr, nullptr};
+    MatchGPULib m(fake_argv[2] ? 3 : 1, fake_argv);  // argv[2] = foveatelevel (MatchGPULib.cpp:259-264)
     float gk[KERNEL_LENGTH], ak[KERNEL_LENGTH] = {0.0, 0.3333, 0.3333, 0.3333, 0.0};
     m.gaussiankernel(gk);
     setConvolutionKernel(gk);
@@ -74,6 +76,26 @@ int main(int argc, char** argv) {
         float* P[3] = {in.data(), in.data() + n, in.data() + 2 * n};
         float** out = m.subsampleDisp(P, (float)(1 / SCALE), 3, W, H, W2, H2);
         wr(argv[7], out, 3, (size_t)W2 * H2);
+    } else if (mode == "hier") {
+        int W = atoi(argv[2]), H = atoi(argv[3]), fl = atoi(argv[4]);
+        int w[16], h[16];
+        w[0] = W;
+        h[0] = H;
+        for (int i = 0; i < fl; i++) {
+            w[i + 1] = w[i] / SCALE;
+            h[i + 1] = h[i] / SCALE;
+        }
+        int fw = w[fl - 1], fh = h[fl - 1];
+        size_t n = (size_t)fw * fh;
+        std::vector<float> in = rd(argv[5], 3 * fl * n);
+        std::vector<float**> lv(fl);
+        std::vector<std::vector<float*>> pl(fl, std::vector<float*>(3));
+        for (int i = 0; i < fl; i++) {
+            for (int k = 0; k < 3; k++) pl[i][k] = in.data() + ((size_t)k * fl + i) * n;
+            lv[i] = pl[i].data();
+        }
+        float** out = m.hierarchicalDisparity(nullptr, lv.data(), 3, W, H);
+        wr(argv[6], out, 3, (size_t)W * H);
     } else {
         return 2;
     }

@@ -635,3 +635,72 @@ int ugsmo_match_foveated(const ugsmo_config* cfg, const uint8_t* rgbL, const uin
     free_pyramid(&pr, levels);
     return 0;
 }
+
+/* ML:435-464: tex2D(src, x / scalefactor, y / scalefactor) * scalefactor, float division and multiply. */
+void ugsmo_partsubsample_disp(const float* src, int w, int h, float scale, float* dst, int w2, int h2) {
+#pragma omp parallel for schedule(static)
+    for (int iy = 0; iy < h2; iy++) {
+        float y = (float)iy + 0.5f;
+        int sy = tex_index(y / scale, h);
+        for (int ix = 0; ix < w2; ix++) {
+            float x = (float)ix + 0.5f;
+            int sx = tex_index(x / scale, w);
+            dst[(size_t)iy * w2 + ix] = scale * src[(size_t)sy * w + sx];
+        }
+    }
+}
+
+/* MGL:2589-2701.  Start from the (uncropped) level fl-1; for level = fl-1 .. 1: upsample the composite to
+ * level-1 dims with levelscale = (float)SCALE (MGL:2638, 2666), then paste the fovea of level-1 at
+ * (l1, u) = (w/2 - fovW/2, h/2 - fovH/2) (MGL:2643-2647, 2678-2683).  H, V and C are treated alike. */
+void ugsmo_composite(const float* stackH, const float* stackV, const float* stackC, int cols, int rows, int levels,
+                     int fovea_level, float* H, float* V, float* C) {
+    int w[UGSMO_MAX_LEVELS], h[UGSMO_MAX_LEVELS];
+    ugsmo_level_dims(cols, rows, levels, w, h);
+    const int fl = fovea_level, fw = w[fl - 1], fh = h[fl - 1];
+    const float* stack[3] = {stackH, stackV, stackC};
+    float* out[3] = {H, V, C};
+    const float levelscale = SCALE_D;
+    for (int k = 0; k < 3; k++) {
+        size_t n = (size_t)fw * fh;
+        float* cur = (float*)malloc(n * sizeof(float));
+        memcpy(cur, stack[k] + (size_t)(fl - 1) * n, n * sizeof(float));
+        int cw = fw, chh = fh;
+        for (int level = fl - 1; level > 0; level--) {
+            int nw = w[level - 1], nh = h[level - 1];
+            float* nxt = (level == 1) ? out[k] : (float*)malloc((size_t)nw * nh * sizeof(float));
+            ugsmo_partsubsample_disp(cur, cw, chh, levelscale, nxt, nw, nh);
+            int l1 = nw / 2 - fw / 2, u = nh / 2 - fh / 2;
+            for (int i = 0; i < fh; i++)
+                memcpy(nxt + (size_t)(u + i) * nw + l1, stack[k] + (size_t)(level - 1) * n + (size_t)i * fw,
+                       fw * sizeof(float));
+            free(cur);
+            cur = nxt;
+            cw = nw;
+            chh = nh;
+        }
+        if (fl == 1) {
+            memcpy(out[k], cur, n * sizeof(float));
+            free(cur);
+        }
+    }
+}
+
+int ugsmo_match_composite(const ugsmo_config* cfg, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols,
+                          size_t step, float* H, float* V, float* C) {
+    int w[UGSMO_MAX_LEVELS], h[UGSMO_MAX_LEVELS];
+    if (cfg->levels < 1 || cfg->levels > UGSMO_MAX_LEVELS || cfg->fovea_level < 2 || cfg->fovea_level > cfg->levels)
+        return 1;
+    ugsmo_level_dims(cols, rows, cfg->levels, w, h);
+    int fl = cfg->fovea_level, fw = w[fl - 1], fh = h[fl - 1];
+    size_t n = (size_t)fl * fw * fh;
+    float* sH = (float*)malloc(n * sizeof(float));
+    float* sV = (float*)malloc(n * sizeof(float));
+    float* sC = (float*)malloc(n * sizeof(float));
+    int rc = ugsmo_match_foveated(cfg, rgbL, rgbR, rows, cols, step, sH, sV, sC, NULL, NULL);
+    if (rc == 0) ugsmo_composite(sH, sV, sC, cols, rows, cfg->levels, fl, H, V, C);
+    free(sH);
+    free(sV);
+    free(sC);
+    return rc;
+}

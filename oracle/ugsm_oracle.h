@@ -103,6 +103,16 @@ int ugsmo_match_full(const ugsmo_config* cfg, const uint8_t* rgbL, const uint8_t
 int ugsmo_match_foveated(const ugsmo_config* cfg, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols,
                          size_t step, float* stackH, float* stackV, float* stackC, int* fovW, int* fovH);
 
+/* MatchLib.cu:435-464 (partsubsampleDispKernel): dst = s * src[floor((y+.5)/s)][floor((x+.5)/s)], all float */
+void ugsmo_partsubsample_disp(const float* src, int w, int h, float scale, float* dst, int w2, int h2);
+/* MatchGPULib.cpp:2589-2701 (hierarchicalDisparity): stack3 = foveated stack (levels 0..fl-1, each 3 planes of
+ * fovW x fovH, level-major as ugsmo_match_foveated returns it) -> 3 full-resolution planes */
+void ugsmo_composite(const float* stackH, const float* stackV, const float* stackC, int cols, int rows, int levels,
+                     int fovea_level, float* H, float* V, float* C);
+/* MatchGPULib.cpp:303-403 with fov == 1 */
+int ugsmo_match_composite(const ugsmo_config* cfg, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols,
+                          size_t step, float* H, float* V, float* C);
+
 #ifdef __cplusplus
 }
 #endif

@@ -260,3 +260,31 @@ def match_foveated(rgbL, rgbR, cfg=None):
         raise ValueError("ugsmo_match_foveated: invalid arguments")
     assert (ofw.value, ofh.value) == (fw, fh)
     return sH, sV, sC, fw, fh
+
+
+def partsubsample_disp(src, scale, w2, h2):
+    src = _f(src)
+    h, w = src.shape
+    dst = np.empty((h2, w2), np.float32)
+    lib().ugsmo_partsubsample_disp(_ptr(src), w, h, C.c_float(scale), _ptr(dst), w2, h2)
+    return dst
+
+
+def composite(sH, sV, sC, cols, rows, levels=14, fovea_level=7):
+    sH, sV, sC = _f(sH), _f(sV), _f(sC)
+    outs = [np.empty((rows, cols), np.float32) for _ in range(3)]
+    lib().ugsmo_composite(_ptr(sH), _ptr(sV), _ptr(sC), cols, rows, levels, fovea_level, *[_ptr(o) for o in outs])
+    return tuple(outs)
+
+
+def match_composite(rgbL, rgbR, cfg=None):
+    cfg = cfg or default_config()
+    rgbL = np.ascontiguousarray(rgbL, np.uint8)
+    rgbR = np.ascontiguousarray(rgbR, np.uint8)
+    rows, cols, _ = rgbL.shape
+    outs = [np.empty((rows, cols), np.float32) for _ in range(3)]
+    rc = lib().ugsmo_match_composite(C.byref(cfg), _ptr(rgbL), _ptr(rgbR), rows, cols, C.c_size_t(rgbL.strides[0]),
+                                     *[_ptr(o) for o in outs])
+    if rc != 0:
+        raise ValueError("ugsmo_match_composite: invalid arguments")
+    return tuple(outs)

@@ -37,6 +37,21 @@ def stage_inputs():
     return L3, R3, H0, V0, C0
 
 
+HIER = (250, 180, 3)  # width, height, fovea level of the hierarchicalDisparity case
+
+
+def hier_stack():
+    """Random foveated stack [plane][level][fovH][fovW] for HIER."""
+    hw, hh, hfl = HIER
+    ws, hs = [hw], [hh]
+    for _ in range(hfl):
+        ws.append(int(ws[-1] / 1.41421356))
+        hs.append(int(hs[-1] / 1.41421356))
+    fw, fh = ws[hfl - 1], hs[hfl - 1]
+    rng = np.random.default_rng(77)
+    return rng.uniform(-3, 3, (3, hfl, fh, fw)).astype(np.float32)
+
+
 def run(args, tmp):
     exe = os.path.join(ROOT, "oracle", "_ref", "refcuda_stage")
     p = subprocess.run([exe] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
@@ -94,6 +109,21 @@ def main(outdir):
     mine = np.stack(oracle.upsample_state(H0, V0, C0, w2, h2))
     out["updisp"] = ref
     cmp("updisp", ref, mine, st)
+    # ---- hierarchicalDisparity (MatchGPULib.cpp:2589-2701) on a random foveated stack, fovea level 3 ----
+    hw, hh, hfl = HIER
+    ws, hs = [hw], [hh]
+    for _ in range(hfl):
+        ws.append(int(ws[-1] / 1.41421356))
+        hs.append(int(hs[-1] / 1.41421356))
+    stack = hier_stack()
+    stack.tofile(tmp + "/in.f32")
+    run(["hier", hw, hh, hfl, tmp + "/in.f32", tmp + "/out.f32"], tmp)
+    ref = np.fromfile(tmp + "/out.f32", np.float32).reshape(3, hh, hw)
+    fw, fh = ws[hfl - 1], hs[hfl - 1]
+    mine = np.stack(oracle.composite(stack[0].reshape(hfl * fh, fw), stack[1].reshape(hfl * fh, fw),
+                                     stack[2].reshape(hfl * fh, fw), hw, hh, levels=hfl + 2, fovea_level=hfl))
+    out["hier"] = ref
+    cmp("hier", ref, mine, st)
     # ---- the same two stages at an UNALIGNED size (250x120): this is where the reference's partial-tile
     # overflow writes / unguarded reads kick in.  Not stored as golden (racy in the reference); only the
     # location of the differences is recorded, as evidence of why full-pipeline agreement is limited.

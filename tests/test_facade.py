@@ -86,6 +86,7 @@ def test_python_mirror(capi, oracle):
     assert (lf[8] == pyr[8]).all()
     H, V, C = m.match(L, R, 0)
     assert H.shape == (816, 1232)
-    with pytest.raises(capi.UgsmError):
-        m.match(L, R, 1)
+    Hc, Vc, Cc = m.match(L, R, 1)  # foveated + hierarchicalDisparity composite
+    want = oracle.match_composite(L, R)
+    assert (Hc == want[0]).all() and (Vc == want[1]).all() and (Cc == want[2]).all()
     m.close()

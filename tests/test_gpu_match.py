@@ -144,3 +144,32 @@ def test_error_paths(capi):
             capi.Handle().match_full(np.zeros((2, 2, 3), np.uint8), np.zeros((2, 2, 3), np.uint8))
         # the handle survives an error
         h.match_full(L, L)
+
+
+def test_composite_stage_bit_exact(capi, oracle):
+    """K4 chain (hierarchicalDisparity) on a random foveated stack vs the oracle."""
+    rng = np.random.default_rng(5)
+    rows, cols, levels, fl = 480, 640, 7, 3
+    w, h = oracle.level_dims(cols, rows, levels)
+    fw, fh = w[fl - 1], h[fl - 1]
+    sH, sV, sC = (rng.uniform(-3, 3, (fl * fh, fw)).astype(np.float32) for _ in range(3))
+    with capi.Handle(levels=levels, fovea_level=fl) as hd:
+        got = hd.stage_composite(sH, sV, sC, rows, cols)
+    want = oracle.composite(sH, sV, sC, cols, rows, levels, fl)
+    _cmp(got, want, "composite stage")
+
+
+def test_match_composite_fov1(capi, oracle):
+    """MatchGPULib::match(L, R, fov = 1): foveated match + hierarchical composite, reduced config and
+    reference defaults."""
+    L, R, _, _ = synth.make_pair(640, 480, 3)
+    kw = dict(levels=7, fovea_level=3)
+    with capi.Handle(**kw) as hd:
+        got = hd.match_composite(L, R)
+    want = oracle.match_composite(L, R, oracle.default_config(**kw))
+    _cmp(got, want, "match(fov=1) 640x480")
+    L, R, _, _ = synth.make_pair(1232, 816, 6)
+    with capi.Handle(max_iters=4) as hd:
+        got = hd.match_composite(L, R)
+    want = oracle.match_composite(L, R, oracle.default_config(max_iters=4))
+    _cmp(got, want, "match(fov=1) 1232x816")

@@ -83,3 +83,15 @@ def test_recorded_full_pipeline_statistics_are_present():
     assert st["unaligned_level_i0_250x120"]["pct_bit_equal_interior40"] == 100.0
     full = json.load(open(os.path.join(HERE, "golden", "refcuda_1232x816_stats.json")))
     assert full["gpu_vs_oracle_bit_equal_H"] and full["gpu_vs_oracle_bit_equal_V"] and full["gpu_vs_oracle_bit_equal_C"]
+
+
+def test_hierarchical_composite_bit_exact_vs_reference_cuda(oracle, gold):
+    """MatchGPULib::hierarchicalDisparity (MatchGPULib.cpp:2589-2701, partsubsampleDispKernel MatchLib.cu:435-464)."""
+    if "hier" not in gold.files:
+        pytest.skip("golden generated before the composite stage existed")
+    hw, hh, hfl = gen.HIER
+    stack = gen.hier_stack()
+    fh, fw = stack.shape[2:]
+    got = np.stack(oracle.composite(stack[0].reshape(hfl * fh, fw), stack[1].reshape(hfl * fh, fw),
+                                    stack[2].reshape(hfl * fh, fw), hw, hh, levels=hfl + 2, fovea_level=hfl))
+    assert (got == gold["hier"]).all()

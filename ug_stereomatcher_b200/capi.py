@@ -20,6 +20,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM = 0, 1, 2, 3, 4
 SYMBOLS = [
     "ugsm_config_default", "ugsm_create", "ugsm_destroy", "ugsm_last_error", "ugsm_set_stream", "ugsm_query_dims",
     "ugsm_match_full", "ugsm_match_foveated", "ugsm_match_full_device", "ugsm_match_foveated_device",
+    "ugsm_match_composite", "ugsm_match_composite_device", "ugsm_stage_composite",
     "ugsm_get_fovea_images", "ugsm_get_pyramid_level", "ugsm_get_level_disparity", "ugsm_get_timing",
     "ugsm_stage_pyramid", "ugsm_stage_correlate", "ugsm_stage_smooth", "ugsm_stage_upsample",
     "ugsm_stage_match_level", "ugsm_bench_correlate", "ugsm_bench_smooth", "ugsm_bench_null", "ugsm_version", "ugsm_band_begin",
@@ -115,6 +116,9 @@ def lib():
         L.ugsm_match_full.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp]
         L.ugsm_match_foveated.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp, C.POINTER(i), C.POINTER(i)]
         L.ugsm_match_full_device.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp]
+        L.ugsm_match_composite.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp]
+        L.ugsm_match_composite_device.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp]
+        L.ugsm_stage_composite.argtypes = [vp, vp, vp, vp, i, i, vp, vp, vp]
         L.ugsm_match_foveated_device.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp]
         L.ugsm_get_fovea_images.argtypes = [vp, i, vp, vp]
         L.ugsm_get_pyramid_level.argtypes = [vp, i, vp, vp]
@@ -232,6 +236,24 @@ class Handle:
         self._ck(lib().ugsm_match_foveated(self._h, _p(rgbL), _p(rgbR), rows, cols, rgbL.strides[0], _p(sH), _p(sV),
                                            _p(sC), C.byref(fw), C.byref(fh)))
         return sH, sV, sC, fw.value, fh.value
+
+    def match_composite(self, rgbL, rgbR):
+        """MatchGPULib::match(L, R, fov=1): foveated match + hierarchical composite -> full-resolution H, V, C."""
+        rgbL = np.ascontiguousarray(rgbL, np.uint8)
+        rgbR = np.ascontiguousarray(rgbR, np.uint8)
+        rows, cols, ch = rgbL.shape
+        if ch != 3 or rgbR.shape != rgbL.shape:
+            raise UgsmError(ERR_INVALID, "expected two (rows, cols, 3) uint8 images of equal shape")
+        H, V, Cc = (np.empty((rows, cols), np.float32) for _ in range(3))
+        self._ck(lib().ugsm_match_composite(self._h, _p(rgbL), _p(rgbR), rows, cols, rgbL.strides[0], _p(H), _p(V),
+                                            _p(Cc)))
+        return H, V, Cc
+
+    def stage_composite(self, sH, sV, sC, rows, cols):
+        sH, sV, sC = map(_f32, (sH, sV, sC))
+        H, V, Cc = (np.empty((rows, cols), np.float32) for _ in range(3))
+        self._ck(lib().ugsm_stage_composite(self._h, _p(sH), _p(sV), _p(sC), rows, cols, _p(H), _p(V), _p(Cc)))
+        return H, V, Cc
 
     # -- whole-pair calls, device pointers (ints) ----------------------------------------
     def match_full_device(self, d_rgbL, d_rgbR, rows, cols, step, dH, dV, dC):

@@ -81,16 +81,14 @@ int MatchGPULib::initStack(int rows, int cols) {
 // MatchGPULib.cpp:303-403
 float** MatchGPULib::match(const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step, int fov) {
     foveatedmatching = fov;
-    if (fov != 0) {
-        snprintf(err_, sizeof err_, "match(fov=1) (hierarchicalDisparity) is outside this path; use matchStackPyramid");
-        fprintf(stderr, "MatchGPULib: %s\n", err_);
-        return nullptr;
-    }
     if (!ensure()) return nullptr;
     size_t n = (size_t)rows * cols;
     float** out = (float**)malloc(3 * sizeof(float*));
     for (int k = 0; k < 3; k++) out[k] = (float*)malloc(n * sizeof(float));
-    if (ugsm_match_full(h_, rgbL, rgbR, rows, cols, step, out[0], out[1], out[2]) != UGSM_OK) {
+    // fov == 1: foveated matching + hierarchicalDisparity composite (MatchGPULib.cpp:355-360)
+    int rc = fov ? ugsm_match_composite(h_, rgbL, rgbR, rows, cols, step, out[0], out[1], out[2])
+                 : ugsm_match_full(h_, rgbL, rgbR, rows, cols, step, out[0], out[1], out[2]);
+    if (rc != UGSM_OK) {
         snprintf(err_, sizeof err_, "%s", ugsm_last_error(h_));
         fprintf(stderr, "MatchGPULib: %s\n", err_);
         for (int k = 0; k < 3; k++) free(out[k]);

@@ -84,6 +84,9 @@ struct ugsm_handle {
     // CUDA graph of the per-pair launch sequence (pyramid levels .. last level), valid for the current shape
     cudaGraphExec_t graph_exec = nullptr;
     int graph_launches = 0;
+    // hierarchicalDisparity composites: 3 planes per level below the fovea level (natural dims), lazily allocated
+    void* comp_arena = nullptr;
+    float* comp[UGSM_MAX_LEVELS][3] = {};
 };
 
 namespace {
@@ -326,6 +329,8 @@ void launch_copy3(ugsm_handle* h, const float* s0, const float* s1, const float*
 void release_shape(ugsm_handle* h) {
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     h->graph_exec = nullptr;
+    if (h->comp_arena) cudaFree(h->comp_arena);
+    h->comp_arena = nullptr;
     if (h->arena) cudaFree(h->arena);
     h->arena = nullptr;
     h->arena_bytes = 0;
@@ -647,6 +652,52 @@ int emit_stack(ugsm_handle* h, float* sH, float* sV, float* sC) {
     return UGSM_OK;
 }
 
+// MGL:2589-2701 on the state the foveated run left in the level buffers; result in comp[0].
+int run_composite(ugsm_handle* h) {
+    const int fl = h->cfg.fovea_level;
+    if (h->mode != 1 || fl < 2) return fail(h, UGSM_ERR_INVALID, "composite needs a foveated run");
+    if (!h->comp_arena) {
+        size_t total = 0;
+        for (int i = 0; i < fl - 1; i++) total += 3 * (((size_t)h->lv[i].pitch * h->lv[i].h * sizeof(float) + 255) / 256 * 256);
+        CK(cudaMalloc(&h->comp_arena, total));
+        char* cur = static_cast<char*>(h->comp_arena);
+        for (int i = 0; i < fl - 1; i++)
+            for (int k = 0; k < 3; k++) {
+                h->comp[i][k] = reinterpret_cast<float*>(cur);
+                cur += ((size_t)h->lv[i].pitch * h->lv[i].h * sizeof(float) + 255) / 256 * 256;
+            }
+    }
+    const float levelscale = SCALE_D;  // MGL:2638 (double) -> float parameter of partsubsampleDispGPU
+    for (int level = fl - 1; level > 0; level--) {
+        LevelBuf& c = h->lv[level];      // coarser level
+        LevelBuf& b = h->lv[level - 1];  // this level: fovea state b.st (b.mw x b.mh), natural dims b.w x b.h
+        K4Planes pl;
+        int pw, ph, pp;
+        if (level == fl - 1) {
+            pw = c.mw, ph = c.mh, pp = c.mpitch;
+        } else {
+            pw = c.w, ph = c.h, pp = c.pitch;
+        }
+        for (int k = 0; k < 3; k++) {
+            pl.prev[k] = (level == fl - 1) ? c.st[k] : h->comp[level][k];
+            pl.fov[k] = b.st[k];
+            pl.dst[k] = h->comp[level - 1][k];
+        }
+        dim3 block(32, 8), grid(div_up(b.w, 32), div_up(b.h, 8));
+        k4_composite<<<grid, block, 0, h->stream>>>(pl, pw, ph, pp, b.mw, b.mh, b.mpitch, b.crop_x, b.crop_y, b.w, b.h,
+                                                    b.pitch, levelscale);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    return UGSM_OK;
+}
+int emit_composite(ugsm_handle* h, float* dH, float* dV, float* dC) {
+    LevelBuf& b = h->lv[0];
+    launch_copy3(h, h->comp[0][0], h->comp[0][1], h->comp[0][2], b.pitch, dH, dV, dC, b.w, b.w, b.h);
+    CK(cudaGetLastError());
+    return UGSM_OK;
+}
+
 struct TmpDev {  // scoped device allocations for the ugsm_stage_* entry points
     std::vector<void*> ptrs;
     ~TmpDev() {
@@ -811,12 +862,14 @@ static int match_host(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, 
     if (!h) return UGSM_ERR_INVALID;
     if (!rgbL || !rgbR || !o0 || !o1 || !o2) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
     if (rows < 1 || cols < 1 || step < (size_t)cols * 3) return fail(h, UGSM_ERR_INVALID, "bad rows/cols/step");
+    const bool composite = (mode == 2);
+    if (composite) mode = 1;
     ugsm_dims d;
     int rc = compute_dims(h->cfg, rows, cols, mode, &d);
     if (rc) return fail(h, rc, "invalid shape/config: rows=%d cols=%d mode=%d", rows, cols, mode);
     CK(cudaSetDevice(h->device));
     size_t rgb_bytes = step * (size_t)rows;
-    size_t out_floats = mode == 0 ? (size_t)rows * cols : (size_t)d.stack_rows * d.fov_width;
+    size_t out_floats = (mode == 0 || composite) ? (size_t)rows * cols : (size_t)d.stack_rows * d.fov_width;
     rc = ensure_staging(h, rgb_bytes, out_floats);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev[3], h->stream));
@@ -824,8 +877,15 @@ static int match_host(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, 
     CK(cudaMemcpyAsync(h->d_rgb[1], rgbR, rgb_bytes, cudaMemcpyHostToDevice, h->stream));
     rc = run_pair(h, h->d_rgb[0], h->d_rgb[1], rows, cols, step, mode);
     if (rc) return rc;
-    rc = mode == 0 ? emit_full(h, h->d_out[0], h->d_out[1], h->d_out[2])
-                   : emit_stack(h, h->d_out[0], h->d_out[1], h->d_out[2]);
+    if (composite) {
+        rc = run_composite(h);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev[2], h->stream));  // the composite belongs to the pair's device time
+        rc = emit_composite(h, h->d_out[0], h->d_out[1], h->d_out[2]);
+    } else {
+        rc = mode == 0 ? emit_full(h, h->d_out[0], h->d_out[1], h->d_out[2])
+                       : emit_stack(h, h->d_out[0], h->d_out[1], h->d_out[2]);
+    }
     if (rc) return rc;
     float* outs[3] = {o0, o1, o2};
     for (int k = 0; k < 3; k++)
@@ -850,6 +910,49 @@ int ugsm_match_full(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, in
 int ugsm_match_foveated(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step,
                         float* stackH, float* stackV, float* stackC, int* fovW, int* fovH) {
     return match_host(h, rgbL, rgbR, rows, cols, step, 1, stackH, stackV, stackC, fovW, fovH);
+}
+
+int ugsm_match_composite(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step,
+                         float* H, float* V, float* C) {
+    return match_host(h, rgbL, rgbR, rows, cols, step, 2, H, V, C, nullptr, nullptr);
+}
+
+int ugsm_match_composite_device(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int rows, int cols,
+                                size_t step, float* dH, float* dV, float* dC) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!dH || !dV || !dC) return fail(h, UGSM_ERR_INVALID, "null output pointer");
+    int rc = run_pair(h, d_rgbL, d_rgbR, rows, cols, step, 1);
+    if (rc) return rc;
+    rc = run_composite(h);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    rc = emit_composite(h, dH, dV, dC);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->timing.h2d_ms = h->timing.d2h_ms = 0;
+    return finish_timing(h);
+}
+
+int ugsm_stage_composite(ugsm_handle* h, const float* stackH, const float* stackV, const float* stackC, int rows,
+                         int cols, float* H, float* V, float* C) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!stackH || !stackV || !stackC || !H || !V || !C) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+    CK(cudaSetDevice(h->device));
+    int rc = prepare_shape(h, rows, cols, 1);
+    if (rc) return rc;
+    const int fl = h->cfg.fovea_level;
+    const float* stack[3] = {stackH, stackV, stackC};
+    for (int i = 0; i < fl; i++) {
+        LevelBuf& b = h->lv[i];
+        size_t off = (size_t)i * b.mw * b.mh;
+        for (int k = 0; k < 3; k++) CK(up2d(b.st[k], b.mpitch, stack[k] + off, b.mw, b.mh, h->stream));
+    }
+    rc = run_composite(h);
+    if (rc) return rc;
+    float* out[3] = {H, V, C};
+    for (int k = 0; k < 3; k++) CK(down2d(out[k], h->comp[0][k], h->lv[0].pitch, h->lv[0].w, h->lv[0].h, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return UGSM_OK;
 }
 
 int ugsm_get_pyramid_level(ugsm_handle* h, int level, float* left3, float* right3) {

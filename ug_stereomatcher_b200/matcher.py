@@ -42,9 +42,8 @@ class MatchGPULib:
     def match(self, rgbL, rgbR, fov=0):
         """-> [H, V, C], each (rows, cols) float32 (MatchGPULib.cpp:303-403)."""
         self.foveatedmatching = fov
-        if fov:
-            raise capi.UgsmError(capi.ERR_INVALID, "match(fov=1) (hierarchicalDisparity) is outside this path; "
-                                                   "use matchStackPyramid")
+        if fov:  # foveated matching + hierarchicalDisparity composite (MatchGPULib.cpp:355-360)
+            return list(self._h.match_composite(rgbL, rgbR))
         return list(self._h.match_full(rgbL, rgbR))
 
     def initStack(self, rgbL, rgbR=None):
