@@ -173,3 +173,25 @@ def test_match_composite_fov1(capi, oracle):
         got = hd.match_composite(L, R)
     want = oracle.match_composite(L, R, oracle.default_config(max_iters=4))
     _cmp(got, want, "match(fov=1) 1232x816")
+
+
+def test_16mp_full_and_foveated_bit_exact(capi, oracle):
+    """BASELINE configs[2] and configs[3] at their full size (4928x3264, reference defaults): the oracle needs a
+    few seconds on the GPU box's host cores, so the full-size result is compared directly, bit for bit; plus the
+    size-independent properties (determinism across handles / graph vs stream launches)."""
+    L, R, dH, dV = synth.make_pair(4928, 3264, 0)
+    with capi.Handle() as h:
+        got = h.match_full(L, R)
+        again = h.match_full(L, R)
+        fov = h.match_foveated(L, R)
+    with capi.Handle(use_graph=0) as h2:
+        nograph = h2.match_full(L, R)
+    for a, b, c in zip(got, again, nograph):
+        assert (a == b).all() and (a == c).all()
+    want = oracle.match_full(L, R)
+    _cmp(got, want, "16MP full")
+    m = (slice(64, -64), slice(64, -64))
+    assert np.abs(got[0] - dH)[m].mean() < 0.35 and np.abs(got[1] - dV)[m].mean() < 0.35  # sanity EPE only
+    wH, wV, wC, fw, fh = oracle.match_foveated(L, R)
+    assert (fw, fh) == (615, 407) == (fov[3], fov[4]) and fov[0].shape == (7 * 407, 615)
+    _cmp(fov[:3], (wH, wV, wC), "16MP foveated")
