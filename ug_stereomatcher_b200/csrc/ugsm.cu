@@ -84,6 +84,9 @@ struct ugsm_handle {
     // CUDA graph of the per-pair launch sequence (pyramid levels .. last level), valid for the current shape
     cudaGraphExec_t graph_exec = nullptr;
     int graph_launches = 0;
+    // same for the row-band path: pyramid + levels [levels-1 .. band_split] + upsample into band_split-1
+    cudaGraphExec_t band_graph = nullptr;
+    int band_graph_split = -1, band_graph_launches = 0;
     // hierarchicalDisparity composites: 3 planes per level below the fovea level (natural dims), lazily allocated
     void* comp_arena = nullptr;
     float* comp[UGSM_MAX_LEVELS][3] = {};
@@ -329,6 +332,9 @@ void launch_copy3(ugsm_handle* h, const float* s0, const float* s1, const float*
 void release_shape(ugsm_handle* h) {
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     h->graph_exec = nullptr;
+    if (h->band_graph) cudaGraphExecDestroy(h->band_graph);
+    h->band_graph = nullptr;
+    h->band_graph_split = -1;
     if (h->comp_arena) cudaFree(h->comp_arena);
     h->comp_arena = nullptr;
     if (h->arena) cudaFree(h->arena);
@@ -1184,13 +1190,47 @@ int ugsm_band_begin(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR
     h->launches = 0;
     h->kev_used = 0;
     unpack_images(h, d_rgbL, d_rgbR, step);
-    build_pyramid(h, 2);
-    prepare_levels(h);
-    rc = run_levels(h, levels - 1, split_levels, false);
-    if (rc) return rc;
-    LevelBuf& c = h->lv[split_levels];
-    LevelBuf& b = h->lv[split_levels - 1];
-    launch_k3(h, c.st, c.mw, c.mh, c.mpitch, 0, 0, b.st, b.mw, b.mh, b.mpitch);
+    auto replicated = [&]() -> int {
+        build_pyramid(h, 2);
+        prepare_levels(h);
+        int r = run_levels(h, levels - 1, split_levels, false);
+        if (r) return r;
+        LevelBuf& c = h->lv[split_levels];
+        LevelBuf& b = h->lv[split_levels - 1];
+        launch_k3(h, c.st, c.mw, c.mh, c.mpitch, 0, 0, b.st, b.mw, b.mh, b.mpitch);
+        return UGSM_OK;
+    };
+    if (!h->cfg.use_graph) {
+        rc = replicated();
+        if (rc) return rc;
+    } else {
+        if (h->band_graph && h->band_graph_split != split_levels) {
+            cudaGraphExecDestroy(h->band_graph);
+            h->band_graph = nullptr;
+        }
+        if (!h->band_graph) {
+            const int l0 = h->launches;
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+            rc = replicated();
+            cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+            if (rc || e != cudaSuccess || !g) {
+                if (g) cudaGraphDestroy(g);
+                return rc ? rc : fail(h, UGSM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+            }
+            e = cudaGraphInstantiate(&h->band_graph, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) {
+                h->band_graph = nullptr;
+                return fail(h, UGSM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+            }
+            h->band_graph_split = split_levels;
+            h->band_graph_launches = h->launches - l0;
+            h->launches = l0;
+        }
+        CK(cudaGraphLaunch(h->band_graph, h->stream));
+        h->launches += h->band_graph_launches;
+    }
     CK(cudaGetLastError());
     return UGSM_OK;
 }
