@@ -12,11 +12,12 @@ N > 1: pairs are independent units, so ranks run data-parallel with no collectiv
 path ("scaling": "weak"); torch.distributed (NCCL) is only the barrier and the max over ranks.
 
   value     pairs/s with the RGB inputs and the outputs resident in HBM (ugsm_match_full_device);
-            one step = 2 pairs per GPU, in flight together on two handles/streams (pairs are
-            independent units; this hides the latency-bound coarse levels of one pair behind
-            the other).  config.ms_per_pair_latency_device is the one-pair-in-flight latency.
+            one step = a batch of 4 pairs per GPU, in flight together on four handles/streams
+            (pairs are independent units; this hides the latency-bound coarse levels of one
+            pair -- and, end to end, the PCIe copies -- behind the others).
+            config.ms_per_pair_latency_device is the one-pair-in-flight latency.
   e2e       pairs/s through the host-buffer C-ABI call (ugsm_match_full) with pinned host
-            buffers: H2D of both images and D2H of H,V,C inside the timed region, same 2 in flight
+            buffers: H2D of both images and D2H of H,V,C inside the timed region, same batch in flight
   roofline  dominant kernel = K1 (fused warp+correlation+fit) at level 0, algorithmic bytes
             48 B/pixel (9 planes in, 3 out) / average launch time from CUDA
             events recorded around every K1 launch of the timed steps, vs MEASURED_PEAKS.json
@@ -39,7 +40,7 @@ METRIC = "16MP_full_pyramid_HV_disparity_throughput"
 UNIT = "pairs/s"
 K1_BYTES_PER_PIXEL = 48  # L x3 + R x3 + (H,V,C) in, (H,V,C) out, f32
 PIXEL_ITERS_16MP = 131429636
-IN_FLIGHT = 2  # pairs in flight per GPU in the throughput regions (independent handles/streams)
+IN_FLIGHT = int(os.environ.get("UGSM_BENCH_IN_FLIGHT", "4"))  # pairs in flight per GPU in the throughput regions (independent handles/streams)
 
 
 def _peaks():
