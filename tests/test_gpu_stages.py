@@ -194,3 +194,29 @@ def test_smooth_special_values_bit_exact(gpu, oracle):
         want = oracle.smooth(H2, V2, C2, 5)
         for g, w, n in zip(got, want, "HVC"):
             _assert_same_away_from_nonfinite(g, w, "smooth specials %s %s" % (n, shape))
+
+
+@pytest.mark.parametrize("shape", [(64, 90), (300, 500), (700, 1100)])
+def test_correlate_black_and_dark_regions_bit_exact(gpu, oracle, shape):
+    """The NCC^2 divisions use a grouped, guarded fast path.  Black regions (0/0 -> NaN -> flat parabola branch,
+    x/0 -> inf -> clamped to 1), very dark regions and a saturated region must take the right path and match the
+    oracle bit for bit in both K1 variants (small / large levels)."""
+    rows, cols = shape
+    rng = np.random.default_rng(rows + cols)
+    L, R, _, _ = synth.make_pair(cols, rows, 2)
+    L3, R3 = _planes(L), _planes(R)
+    L3[:, 10:30, 20:60] = 0.0           # black in the left image only
+    R3[:, 25:50, 40:80] = 0.0           # black in the right image, partly overlapping
+    L3[:, rows // 2:rows // 2 + 12, :] = 0.0
+    R3[:, rows // 2:rows // 2 + 12, :] = 0.0   # black in both
+    L3[:, -20:, -40:] = 1.0             # very dark
+    R3[:, -20:, -40:] = 1.0
+    L3[:, :8, :8] = 255.0
+    R3[:, :8, :8] = 255.0
+    L3[1, 40:44, 5:9] = 1e-12           # tiny (a blurred, almost black coarse level)
+    R3[1, 40:44, 5:9] = 1e-12
+    H, V, C = _state(rng, rows, cols)
+    got = gpu.stage_correlate(L3, R3, H, V, C, 1.0, False, debug=True)
+    want = oracle.correlate(L3, R3, H, V, C, 1.0, False, debug=True)
+    for g, w, n in zip(got, want, ["Hn", "Vn", "Cn", "srcx", "srcy", "branchH", "branchV"]):
+        _assert_same(g, w, "%s %dx%d with black regions" % (n, cols, rows))
