@@ -165,6 +165,9 @@ int ugsm_stage_upsample(ugsm_handle* h, const float* H, const float* V, const fl
                         int fine_w, int fine_h, int crop_x, int crop_y, int out_w, int out_h, float* Ho, float* Vo,
                         float* Co);
 
+/* The parabola fit K1 uses (PolyDisparity, MatchLib.cu:790-843) on n (l, c, r) triples. */
+int ugsm_stage_poly(ugsm_handle* h, const float* l, const float* c, const float* r, int n, float T, float* offset,
+                    float* conf, uint8_t* branch);
 /* K4 chain: hierarchicalDisparity on a given foveated stack (layout of ugsm_match_foveated). */
 int ugsm_stage_composite(ugsm_handle* h, const float* stackH, const float* stackV, const float* stackC, int rows,
                          int cols, float* H, float* V, float* C);

@@ -260,6 +260,12 @@ void ugsmo_poly(float l, float c, float r, float T, float* offset, float* conf, 
     }
 }
 
+void ugsmo_poly_n(const float* l, const float* c, const float* r, int n, float T, float* offset, float* conf,
+                  uint8_t* branch) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) ugsmo_poly(l[i], c[i], r[i], T, &offset[i], &conf[i], &branch[i]);
+}
+
 /* ML:1092-1145: five-point confidence-weighted average, centre, x-1, x+1, y-1, y+1 in
  * that order; row 0 and column 0 are not written (caller pre-fills dst with src). */
 void ugsmo_smooth_pass(const float* src, const float* conf, float* dst, int w, int h) {

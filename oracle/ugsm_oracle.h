@@ -77,6 +77,9 @@ void ugsmo_warp(const float* R, const float* H, const float* V, int w, int h, fl
                 int32_t* srcy);
 /* MatchLib.cu:790-843 */
 void ugsmo_poly(float l, float c, float r, float T, float* offset, float* conf, uint8_t* branch);
+/* ugsmo_poly on n triples */
+void ugsmo_poly_n(const float* l, const float* c, const float* r, int n, float T, float* offset, float* conf,
+                  uint8_t* branch);
 /* MatchLib.cu:1092-1145 */
 void ugsmo_smooth_pass(const float* src, const float* conf, float* dst, int w, int h);
 

@@ -288,3 +288,11 @@ def match_composite(rgbL, rgbR, cfg=None):
     if rc != 0:
         raise ValueError("ugsmo_match_composite: invalid arguments")
     return tuple(outs)
+
+
+def poly_n(l, c, r, T):
+    l, c, r = _f(l), _f(c), _f(r)
+    n = l.size
+    off, conf, br = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.uint8)
+    lib().ugsmo_poly_n(_ptr(l), _ptr(c), _ptr(r), n, C.c_float(T), _ptr(off), _ptr(conf), _ptr(br))
+    return off, conf, br

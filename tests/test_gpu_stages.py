@@ -220,3 +220,32 @@ def test_correlate_black_and_dark_regions_bit_exact(gpu, oracle, shape):
     want = oracle.correlate(L3, R3, H, V, C, 1.0, False, debug=True)
     for g, w, n in zip(got, want, ["Hn", "Vn", "Cn", "srcx", "srcy", "branchH", "branchV"]):
         _assert_same(g, w, "%s %dx%d with black regions" % (n, cols, rows))
+
+
+@pytest.mark.parametrize("T", [1.0, 0.55, 0.1])
+def test_poly_fit_exhaustive_bit_exact(gpu, oracle, T):
+    """K1's parabola fit replaces the reference's double division by a guarded f32 fast path (double rounding is
+    innocuous for f32 operands) -- compare millions of triples, including ties, tiny/huge/zero/NaN values and the
+    rescale branch, with the oracle's literal double arithmetic."""
+    rng = np.random.default_rng(int(T * 100))
+    n = 2_000_000
+    l, c, r = (rng.uniform(0, 1, n).astype(np.float32) for _ in range(3))
+    # near-flat and near-symmetric cases, where c1 ~ 0 and b1 ~ 0
+    k = n // 4
+    l[:k] = c[:k] + rng.normal(0, 1e-6, k).astype(np.float32)
+    r[:k] = c[:k] + rng.normal(0, 1e-6, k).astype(np.float32)
+    r[k:2 * k] = l[k:2 * k]
+    # peaks above 1 (rescale branch): centre near 1, neighbours close
+    c[2 * k:2 * k + 50000] = 1.0
+    l[2 * k:2 * k + 50000] = rng.uniform(0.9, 1.0, 50000)
+    r[2 * k:2 * k + 50000] = rng.uniform(0.9, 1.0, 50000)
+    specials = np.array([0.0, 1.0, 1e-45, 1e-40, 1e-38, 1e-30, 1e-20, 1e-10, 0.5, np.nan, 2.0 ** -62, 2.0 ** -63,
+                         2.0 ** -126, 3e-39], np.float32)
+    idx = rng.integers(0, n, 300000)
+    for arr in (l, c, r):
+        arr[idx[rng.integers(0, len(idx), 100000)]] = specials[rng.integers(0, len(specials), 100000)]
+    got = gpu.stage_poly(l, c, r, T)
+    want = oracle.poly_n(l, c, r, T)
+    for g, w, name in zip(got, want, ["offset", "conf", "branch"]):
+        _assert_same(g, w, "poly %s T=%g" % (name, T))
+    assert (want[2] == 2).sum() > 1000 and (want[2] == 1).sum() > 100000 and (want[2] == 0).sum() > 100000

@@ -20,7 +20,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM = 0, 1, 2, 3, 4
 SYMBOLS = [
     "ugsm_config_default", "ugsm_create", "ugsm_destroy", "ugsm_last_error", "ugsm_set_stream", "ugsm_query_dims",
     "ugsm_match_full", "ugsm_match_foveated", "ugsm_match_full_device", "ugsm_match_foveated_device",
-    "ugsm_match_composite", "ugsm_match_composite_device", "ugsm_stage_composite",
+    "ugsm_match_composite", "ugsm_match_composite_device", "ugsm_stage_composite", "ugsm_stage_poly",
     "ugsm_get_fovea_images", "ugsm_get_pyramid_level", "ugsm_get_level_disparity", "ugsm_get_timing",
     "ugsm_stage_pyramid", "ugsm_stage_correlate", "ugsm_stage_smooth", "ugsm_stage_upsample",
     "ugsm_stage_match_level", "ugsm_bench_correlate", "ugsm_bench_smooth", "ugsm_bench_null", "ugsm_version", "ugsm_band_begin",
@@ -119,6 +119,7 @@ def lib():
         L.ugsm_match_composite.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp]
         L.ugsm_match_composite_device.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp]
         L.ugsm_stage_composite.argtypes = [vp, vp, vp, vp, i, i, vp, vp, vp]
+        L.ugsm_stage_poly.argtypes = [vp, vp, vp, vp, i, C.c_float, vp, vp, vp]
         L.ugsm_match_foveated_device.argtypes = [vp, vp, vp, i, i, sz, vp, vp, vp]
         L.ugsm_get_fovea_images.argtypes = [vp, i, vp, vp]
         L.ugsm_get_pyramid_level.argtypes = [vp, i, vp, vp]
@@ -248,6 +249,13 @@ class Handle:
         self._ck(lib().ugsm_match_composite(self._h, _p(rgbL), _p(rgbR), rows, cols, rgbL.strides[0], _p(H), _p(V),
                                             _p(Cc)))
         return H, V, Cc
+
+    def stage_poly(self, l, c, r, T):
+        l, c, r = map(_f32, (l, c, r))
+        n = l.size
+        off, conf, br = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.uint8)
+        self._ck(lib().ugsm_stage_poly(self._h, _p(l), _p(c), _p(r), n, T, _p(off), _p(conf), _p(br)))
+        return off, conf, br
 
     def stage_composite(self, sH, sV, sC, rows, cols):
         sH, sV, sC = map(_f32, (sH, sV, sC))

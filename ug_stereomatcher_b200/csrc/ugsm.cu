@@ -1407,6 +1407,42 @@ int ugsm_bench_correlate(ugsm_handle* h, int width, int height, int reps, float*
     return UGSM_OK;
 }
 
+__global__ void k_poly_test(const float* l, const float* c, const float* r, float T, float* off, float* conf,
+                            uint8_t* br, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float o, cf;
+    int b;
+    poly_fit(l[i], c[i], r[i], T, o, cf, b);
+    off[i] = o;
+    conf[i] = cf;
+    br[i] = (uint8_t)b;
+}
+
+/* PolyDisparity (ML:790-843) on n (l, c, r) triples: the device function K1 uses, for exhaustive parity tests. */
+int ugsm_stage_poly(ugsm_handle* h, const float* l, const float* c, const float* r, int n, float T, float* offset,
+                    float* conf, uint8_t* branch) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!l || !c || !r || !offset || !conf || !branch || n < 1) return fail(h, UGSM_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    TmpDev td;
+    float* d[5];
+    for (auto& p : d)
+        if (!(p = td.alloc<float>(n))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
+    uint8_t* db = td.alloc<uint8_t>(n);
+    if (!db) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
+    CK(cudaMemcpyAsync(d[0], l, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d[1], c, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d[2], r, n * 4, cudaMemcpyHostToDevice, h->stream));
+    k_poly_test<<<div_up(n, 256), 256, 0, h->stream>>>(d[0], d[1], d[2], T, d[3], d[4], db, n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(offset, d[3], n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(conf, d[4], n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(branch, db, n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return UGSM_OK;
+}
+
 __global__ void k_null(int) {}
 
 /* Launch floor: average time of `reps` back-to-back empty launches on the handle's stream. */
