@@ -213,6 +213,45 @@ int ugsm_band_emit(ugsm_handle* h, float* dH, float* dV, float* dC, int y_begin,
 
 const char* ugsm_version(void);
 
+/* ---- Point cloud from the disparity planes.  K5 replaces the per-pixel host loops of
+ * the reference's point-cloud node, src/pointcloud/getPointCloud.cpp (PC): get3DPoint PC:886-945,
+ * doReconstructionRGB PC:741-782, doReconstructionRGB_FOV PC:697-740 with mapX/Ycoord PC:375-421 and the
+ * margins PC:432-484.  Results are bit-identical to that code (x86-64 host build, no FMA) for finite
+ * disparities; the "resized" clouds (PC:784-884, OpenCV bicubic resize) are not provided. ---- */
+typedef struct ugsm_camera_pair {
+    double P1[12]; /* sensor_msgs/CameraInfo.P of the left camera, row-major 3x4 (PC:1158) */
+    double P2[12]; /* ... of the right camera (PC:1159) */
+} ugsm_camera_pair;
+
+/* Number of points a rows x cols plane yields at this sampling: ceil(cols/s) * ceil(rows/s) (PC:746-759). */
+int ugsm_cloud_count(int rows, int cols, int sampling, int64_t* npoints);
+
+/* Full-resolution cloud (PC:741-782).  H, V: rows*cols floats (the matcher's output planes); img: the left image,
+ * 3 interleaved bytes per pixel, `step` bytes per row, bgr = 1 for B,G,R byte order (the node's cv image), 0 for
+ * R,G,B.  points: npoints records of point_stride floats, in the reference's column-major order (record
+ * (x/s) * ceil(rows/s) + y/s).  point_stride 4: {x, y, z, rgb}; 8: the pcl::PointXYZRGB memory layout
+ * {x, y, z, 1.0f, rgb, 0, 0, 0}.  rgb = the bits of r<<16 | g<<8 | b (PC:770-775).  Host buffers. */
+int ugsm_cloud_full(ugsm_handle* h, const ugsm_camera_pair* cam, const float* H, const float* V, int rows, int cols,
+                    const uint8_t* img, size_t step, int bgr, int sampling, float* points, int point_stride,
+                    int64_t* npoints);
+/* Same with every buffer already in device memory; dH/dV rows are pitch_floats apart; d_points 16-byte aligned. */
+int ugsm_cloud_full_device(ugsm_handle* h, const ugsm_camera_pair* cam, const float* dH, const float* dV,
+                           int pitch_floats, int rows, int cols, const uint8_t* d_img, size_t step, int bgr,
+                           int sampling, float* d_points, int point_stride, int64_t* npoints);
+/* Foveated cloud of stack level src_level (0 = finest fovea; PC:697-740).  stackH/V: the (levels*fov_rows) x
+ * fov_cols stacks ugsm_match_foveated returns; img: the full-resolution im_rows x im_cols left image. */
+int ugsm_cloud_foveated(ugsm_handle* h, const ugsm_camera_pair* cam, const float* stackH, const float* stackV,
+                        int fov_rows, int fov_cols, int src_level, int im_rows, int im_cols, const uint8_t* img,
+                        size_t step, int bgr, int sampling, float* points, int point_stride, int64_t* npoints);
+/* Cloud of the pair last matched on this handle, straight from the planes and the left image still resident in
+ * device memory (no D2H / H2D of the 16 MP planes).  src_level < 0: the full-resolution planes of the last
+ * ugsm_match_full / ugsm_match_composite; src_level >= 0: that level of the last foveated match.  After a
+ * *_device match the caller's left image must still be valid.  points: host (points_on_device = 0) or device. */
+int ugsm_cloud_from_match(ugsm_handle* h, const ugsm_camera_pair* cam, int src_level, int sampling, float* points,
+                          int point_stride, int points_on_device, int64_t* npoints);
+/* Device time of the last cloud kernel (CUDA events on the handle's stream). */
+int ugsm_cloud_last_ms(const ugsm_handle* h, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,1 @@
+#include "pc_stubs.h"  // stand-in for <opencv2/imgproc/imgproc.hpp>: see oracle/refbuild/stubs_pc/pc_stubs.h

@@ -1,0 +1,1 @@
+#include "pc_stubs.h"  // stand-in for <sensor_msgs/Image.h>: see oracle/refbuild/stubs_pc/pc_stubs.h

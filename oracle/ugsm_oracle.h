@@ -116,6 +116,24 @@ void ugsmo_composite(const float* stackH, const float* stackV, const float* stac
 int ugsmo_match_composite(const ugsmo_config* cfg, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols,
                           size_t step, float* H, float* V, float* C);
 
+/* ---- point cloud from H, V (oracle/ugsm_oracle_cloud.c) ---- */
+/* getPointCloud.cpp:886-945 (get3DPoint); P1, P2 = CameraInfo.P of the left / right camera, row-major 3x4 */
+void ugsmo_triangulate(const double P1[12], const double P2[12], float x1, float y1, float x2, float y2,
+                       float out[3]);
+int64_t ugsmo_cloud_count(int rows, int cols, int sampling);
+/* getPointCloud.cpp:741-782 (doReconstructionRGB); points: count x stride floats, stride 4 = {x,y,z,rgb},
+ * stride 8 = pcl::PointXYZRGB layout {x,y,z,1,rgb,0,0,0}; column-major point order; returns the count */
+int64_t ugsmo_cloud_full(const double P1[12], const double P2[12], const float* dX, const float* dY, int rows,
+                         int cols, const uint8_t* img, size_t step, int bgr, int sampling, float* points,
+                         int stride);
+/* getPointCloud.cpp:432-484 (destLevel 0) and 375-421 */
+void ugsmo_cloud_margins(int im_rows, int im_cols, int fovea_level, int src_level, int* left, int* upper);
+float ugsmo_cloud_scale(int src_level);
+/* getPointCloud.cpp:697-740 (doReconstructionRGB_FOV) */
+int64_t ugsmo_cloud_foveated(const double P1[12], const double P2[12], const float* stackX, const float* stackY,
+                             int fov_h, int fov_w, int fovea_level, int src_level, int im_rows, int im_cols,
+                             const uint8_t* img, size_t step, int bgr, int sampling, float* points, int stride);
+
 #ifdef __cplusplus
 }
 #endif

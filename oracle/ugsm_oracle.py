@@ -296,3 +296,95 @@ def poly_n(l, c, r, T):
     off, conf, br = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.uint8)
     lib().ugsmo_poly_n(_ptr(l), _ptr(c), _ptr(r), n, C.c_float(T), _ptr(off), _ptr(conf), _ptr(br))
     return off, conf, br
+
+
+# ---- point cloud (oracle/ugsm_oracle_cloud.c) ----
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+def _cam(P):
+    P = np.ascontiguousarray(P, np.float64).reshape(12)
+    return P
+
+
+def triangulate(P1, P2, x1, y1, x2, y2):
+    out = np.empty(3, np.float32)
+    lib().ugsmo_triangulate(_ptr(_cam(P1)), _ptr(_cam(P2)), C.c_float(x1), C.c_float(y1), C.c_float(x2),
+                            C.c_float(y2), _ptr(out))
+    return out
+
+
+def cloud_count(rows, cols, sampling):
+    f = lib().ugsmo_cloud_count
+    f.restype = C.c_int64
+    return int(f(rows, cols, sampling))
+
+
+def cloud_margins(im_rows, im_cols, fovea_level, src_level):
+    l, u = C.c_int(), C.c_int()
+    lib().ugsmo_cloud_margins(im_rows, im_cols, fovea_level, src_level, C.byref(l), C.byref(u))
+    return l.value, u.value
+
+
+def cloud_scale(src_level):
+    f = lib().ugsmo_cloud_scale
+    f.restype = C.c_float
+    return float(f(src_level))
+
+
+def cloud_full(P1, P2, dX, dY, img, bgr=True, sampling=1, stride=4):
+    """-> (n, stride) float32 records; column 3 (stride 4) / 4 (stride 8) holds the packed rgb bits."""
+    dX, dY = _f(dX), _f(dY)
+    img = np.ascontiguousarray(img, np.uint8)
+    rows, cols = dX.shape
+    n = cloud_count(rows, cols, sampling)
+    pts = np.empty((n, stride), np.float32)
+    f = lib().ugsmo_cloud_full
+    f.restype = C.c_int64
+    got = f(_ptr(_cam(P1)), _ptr(_cam(P2)), _ptr(dX), _ptr(dY), rows, cols, _ptr(img), C.c_size_t(img.strides[0]),
+            int(bgr), sampling, _ptr(pts), stride)
+    if got != n:
+        raise ValueError("ugsmo_cloud_full: invalid arguments")
+    return pts
+
+
+def cloud_foveated(P1, P2, stackX, stackY, fov_h, src_level, im_rows, im_cols, img, fovea_level=7, bgr=True,
+                   sampling=1, stride=4):
+    stackX, stackY = _f(stackX), _f(stackY)
+    img = np.ascontiguousarray(img, np.uint8)
+    fov_w = stackX.shape[1]
+    n = cloud_count(fov_h, fov_w, sampling)
+    pts = np.empty((n, stride), np.float32)
+    f = lib().ugsmo_cloud_foveated
+    f.restype = C.c_int64
+    got = f(_ptr(_cam(P1)), _ptr(_cam(P2)), _ptr(stackX), _ptr(stackY), fov_h, fov_w, fovea_level, src_level,
+            im_rows, im_cols, _ptr(img), C.c_size_t(img.strides[0]), int(bgr), sampling, _ptr(pts), stride)
+    if got != n:
+        raise ValueError("ugsmo_cloud_foveated: invalid arguments")
+    return pts
+
+
+def run_refpc(mode, P1, P2, dX, dY, img, sampling=1, src_level=0, workdir=None):
+    """Run oracle/_ref/refpc (the unmodified reference point-cloud source behind stubs).
+    mode 0: full cloud; mode 1: foveated cloud of stack level src_level.  -> (n, 4) float32."""
+    import struct
+    import tempfile
+
+    exe = os.path.join(_HERE, "_ref", "refpc")
+    if not os.path.exists(exe):
+        raise FileNotFoundError(exe)
+    dX, dY = _f(dX), _f(dY)
+    img = np.ascontiguousarray(img, np.uint8)
+    with tempfile.TemporaryDirectory(dir=workdir) as td:
+        fin, fout = os.path.join(td, "in.bin"), os.path.join(td, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(struct.pack("7i", mode, dX.shape[0], dX.shape[1], img.shape[0], img.shape[1], sampling, src_level))
+            f.write(_cam(P1).tobytes())
+            f.write(_cam(P2).tobytes())
+            f.write(dX.tobytes())
+            f.write(dY.tobytes())
+            f.write(img.tobytes())
+        subprocess.run([exe, fin, fout], check=True)
+        raw = open(fout, "rb").read()
+    n = struct.unpack("q", raw[:8])[0]
+    return np.frombuffer(raw[8:], np.float32).reshape(n, 4).copy()

@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libugsm.so")
+LIB_PATH = os.environ.get("UGSM_LIB") or os.path.join(_HERE, "libugsm.so")  # UGSM_LIB: tuning builds
 MAX_LEVELS = 14
 TIMED_LEVELS = 4
 
@@ -25,7 +25,8 @@ SYMBOLS = [
     "ugsm_stage_pyramid", "ugsm_stage_correlate", "ugsm_stage_smooth", "ugsm_stage_upsample",
     "ugsm_stage_match_level", "ugsm_bench_correlate", "ugsm_bench_smooth", "ugsm_bench_null", "ugsm_version", "ugsm_band_begin",
     "ugsm_band_level_info", "ugsm_band_iteration", "ugsm_band_upsample", "ugsm_band_emit", "ugsm_band_pack",
-    "ugsm_band_unpack",
+    "ugsm_band_unpack", "ugsm_cloud_count", "ugsm_cloud_full", "ugsm_cloud_full_device", "ugsm_cloud_foveated",
+    "ugsm_cloud_from_match", "ugsm_cloud_last_ms",
 ]
 
 
@@ -81,6 +82,18 @@ class BandLevel(C.Structure):
         ("smooth", C.c_int32),
         ("state", C.c_void_p * 3),
     ]
+
+
+class CameraPair(C.Structure):
+    """sensor_msgs/CameraInfo.P of the left and right camera, row-major 3x4 (getPointCloud.cpp:1158-1159)."""
+    _fields_ = [("P1", C.c_double * 12), ("P2", C.c_double * 12)]
+
+    @classmethod
+    def of(cls, P1, P2):
+        c = cls()
+        c.P1[:] = [float(v) for v in np.asarray(P1, np.float64).reshape(12)]
+        c.P2[:] = [float(v) for v in np.asarray(P2, np.float64).reshape(12)]
+        return c
 
 
 class UgsmError(RuntimeError):
@@ -140,6 +153,13 @@ def lib():
         L.ugsm_band_emit.argtypes = [vp, vp, vp, vp, i, i]
         L.ugsm_band_pack.argtypes = [vp, i, i, i, vp]
         L.ugsm_band_unpack.argtypes = [vp, i, i, i, vp]
+        i64p, cam = C.POINTER(C.c_int64), C.POINTER(CameraPair)
+        L.ugsm_cloud_count.argtypes = [i, i, i, i64p]
+        L.ugsm_cloud_full.argtypes = [vp, cam, vp, vp, i, i, vp, sz, i, i, vp, i, i64p]
+        L.ugsm_cloud_full_device.argtypes = [vp, cam, vp, vp, i, i, i, vp, sz, i, i, vp, i, i64p]
+        L.ugsm_cloud_foveated.argtypes = [vp, cam, vp, vp, i, i, i, i, i, vp, sz, i, i, vp, i, i64p]
+        L.ugsm_cloud_from_match.argtypes = [vp, cam, i, i, vp, i, i, i64p]
+        L.ugsm_cloud_last_ms.argtypes = [vp, C.POINTER(C.c_float)]
         _LIB = L
     return _LIB
 
@@ -160,6 +180,13 @@ def query_dims(cfg, rows, cols, mode=0):
     if rc != OK:
         raise UgsmError(rc, "ugsm_query_dims: invalid rows/cols/mode/config")
     return d
+
+
+def cloud_count(rows, cols, sampling=1):
+    n = C.c_int64()
+    if lib().ugsm_cloud_count(rows, cols, sampling, C.byref(n)) != OK:
+        raise UgsmError(ERR_INVALID, "ugsm_cloud_count: invalid rows/cols/sampling")
+    return n.value
 
 
 def _p(a):
@@ -262,6 +289,60 @@ class Handle:
         H, V, Cc = (np.empty((rows, cols), np.float32) for _ in range(3))
         self._ck(lib().ugsm_stage_composite(self._h, _p(sH), _p(sV), _p(sC), rows, cols, _p(H), _p(V), _p(Cc)))
         return H, V, Cc
+
+    # -- point cloud from disparity planes (K5) -------------------------------------------
+    def cloud_full(self, cam, H, V, img, bgr=True, sampling=1, stride=4):
+        """doReconstructionRGB (getPointCloud.cpp:741-782) -> (n, stride) float32 records, column-major order."""
+        H, V = _f32(H), _f32(V)
+        img = np.ascontiguousarray(img, np.uint8)
+        rows, cols = H.shape
+        if V.shape != H.shape or img.shape != (rows, cols, 3):
+            raise UgsmError(ERR_INVALID, "expected H, V of equal shape and a (rows, cols, 3) uint8 image")
+        pts = np.empty((cloud_count(rows, cols, sampling), stride), np.float32)
+        n = C.c_int64()
+        self._ck(lib().ugsm_cloud_full(self._h, C.byref(cam), _p(H), _p(V), rows, cols, _p(img), img.strides[0],
+                                       int(bgr), sampling, _p(pts), stride, C.byref(n)))
+        assert n.value == pts.shape[0]
+        return pts
+
+    def cloud_foveated(self, cam, stackH, stackV, fov_rows, src_level, img, bgr=True, sampling=1, stride=4):
+        """doReconstructionRGB_FOV (getPointCloud.cpp:697-740) for stack level src_level; img = full-res left image."""
+        stackH, stackV = _f32(stackH), _f32(stackV)
+        img = np.ascontiguousarray(img, np.uint8)
+        fov_cols = stackH.shape[1]
+        pts = np.empty((cloud_count(fov_rows, fov_cols, sampling), stride), np.float32)
+        n = C.c_int64()
+        self._ck(lib().ugsm_cloud_foveated(self._h, C.byref(cam), _p(stackH), _p(stackV), fov_rows, fov_cols, src_level,
+                                           img.shape[0], img.shape[1], _p(img), img.strides[0], int(bgr), sampling,
+                                           _p(pts), stride, C.byref(n)))
+        assert n.value == pts.shape[0]
+        return pts
+
+    def cloud_from_match(self, cam, rows, cols, src_level=-1, sampling=1, stride=4, out=None, d_points=None):
+        """Cloud of the pair last matched on this handle, from the device-resident planes.  rows, cols: extent of
+        the planes used (the image for src_level < 0, the fovea otherwise).  d_points: device pointer (int) to
+        write to instead of returning a host array."""
+        n = C.c_int64()
+        if d_points is not None:
+            self._ck(lib().ugsm_cloud_from_match(self._h, C.byref(cam), src_level, sampling, C.c_void_p(d_points),
+                                                 stride, 1, C.byref(n)))
+            return n.value
+        pts = out if out is not None else np.empty((cloud_count(rows, cols, sampling), stride), np.float32)
+        self._ck(lib().ugsm_cloud_from_match(self._h, C.byref(cam), src_level, sampling, _p(pts), stride, 0,
+                                             C.byref(n)))
+        assert n.value == pts.shape[0]
+        return pts
+
+    def cloud_full_device(self, cam, dH, dV, pitch, rows, cols, d_img, step, bgr, sampling, d_points, stride=4):
+        n = C.c_int64()
+        self._ck(lib().ugsm_cloud_full_device(self._h, C.byref(cam), dH, dV, pitch, rows, cols, d_img, step, int(bgr),
+                                              sampling, d_points, stride, C.byref(n)))
+        return n.value
+
+    def cloud_last_ms(self):
+        ms = C.c_float()
+        self._ck(lib().ugsm_cloud_last_ms(self._h, C.byref(ms)))
+        return ms.value
 
     # -- whole-pair calls, device pointers (ints) ----------------------------------------
     def match_full_device(self, d_rgbL, d_rgbR, rows, cols, step, dH, dV, dC):

@@ -14,6 +14,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -90,6 +91,14 @@ struct ugsm_handle {
     // hierarchicalDisparity composites: 3 planes per level below the fovea level (natural dims), lazily allocated
     void* comp_arena = nullptr;
     float* comp[UGSM_MAX_LEVELS][3] = {};
+    // point cloud (K5): what the last match left on the device, and grow-only staging for the host entry points
+    const uint8_t* last_rgbL = nullptr;
+    size_t last_step = 0;
+    int last_kind = -1;  // 0 full, 1 foveated, 2 foveated + composite
+    void* cloud_buf = nullptr;
+    size_t cloud_bytes = 0;
+    cudaEvent_t cloud_ev[2] = {};
+    float cloud_ms = 0.f;
 };
 
 namespace {
@@ -205,6 +214,8 @@ int set_kernel_attrs(ugsm_handle* h) {
                             (int)sizeof(K1Smem<4, K1_TH>)));
     CK(cudaFuncSetAttribute(k1_correlate<2, K1_TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(K1Smem<2, K1_TH>)));
+    CK(cudaFuncSetAttribute(k1_correlate<2, K1_TH>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
     if (const char* e = getenv("UGSM_K1_NW")) h->k1_nw = atoi(e);  // tuning override: warps per K1 CTA (2 or 4)
     CK(cudaFuncSetAttribute(k2_smooth_box, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)k2_smem_bytes(K2_MAX_BH)));
@@ -343,6 +354,7 @@ void release_shape(ugsm_handle* h) {
     h->lv.clear();
     h->rows = h->cols = 0;
     h->mode = -1;
+    h->last_kind = -1;
 }
 
 int prepare_shape(ugsm_handle* h, int rows, int cols, int mode) {
@@ -583,6 +595,9 @@ int run_pair(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int r
     }
     CK(cudaEventRecord(h->ev[2], h->stream));
     CK(cudaGetLastError());
+    h->last_rgbL = d_rgbL;
+    h->last_step = step;
+    h->last_kind = mode;
     return UGSM_OK;
 }
 
@@ -695,6 +710,7 @@ int run_composite(ugsm_handle* h) {
         h->launches++;
     }
     CK(cudaGetLastError());
+    h->last_kind = 2;
     return UGSM_OK;
 }
 int emit_composite(ugsm_handle* h, float* dH, float* dV, float* dC) {
@@ -724,6 +740,78 @@ cudaError_t up2d(float* d, int pitch, const float* hsrc, int w, int hh, cudaStre
 }
 cudaError_t down2d(float* hdst, const float* d, int pitch, int w, int hh, cudaStream_t s) {
     return cudaMemcpy2DAsync(hdst, (size_t)w * 4, d, (size_t)pitch * 4, (size_t)w * 4, hh, cudaMemcpyDeviceToHost, s);
+}
+
+// ---- K5: point cloud (PC = src/pointcloud/getPointCloud.cpp) ----
+// PC:432-484 with destLevel = 0: margin of the fovea of stack level src_level inside the full image.
+void cloud_margins(int im_rows, int im_cols, int fovea_level, int src_level, int* left, int* upper) {
+    int w = im_cols, hh = im_rows;
+    for (int k = 0; k < (fovea_level - 1) - src_level; k++) {
+        w = (int)(w / SCALE_D);
+        hh = (int)(hh / SCALE_D);
+    }
+    *left = im_cols / 2 - w / 2;
+    *upper = im_rows / 2 - hh / 2;
+}
+
+int cloud_events(ugsm_handle* h) {
+    for (auto& ev : h->cloud_ev)
+        if (!ev) CK(cudaEventCreate(&ev));
+    return UGSM_OK;
+}
+
+int ensure_cloud_staging(ugsm_handle* h, size_t bytes) {
+    if (bytes <= h->cloud_bytes) return UGSM_OK;
+    if (h->cloud_buf) cudaFree(h->cloud_buf);
+    h->cloud_buf = nullptr;
+    h->cloud_bytes = 0;
+    CK(cudaMalloc(&h->cloud_buf, bytes));
+    h->cloud_bytes = bytes;
+    return UGSM_OK;
+}
+
+// Launch K5 on device-resident planes.  src_level < 0: full-resolution planes; otherwise the planes are one
+// level of a fovea stack belonging to an im_rows x im_cols image.
+int launch_cloud(ugsm_handle* h, const ugsm_camera_pair* cam, const float* dX, const float* dY, int pitch, int rows,
+                 int cols, int src_level, int im_rows, int im_cols, const uint8_t* d_img, size_t step, int bgr,
+                 int sampling, float* d_points, int stride, int64_t* npoints) {
+    if (!cam || !dX || !dY || !d_img || !d_points) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+    if (rows < 1 || cols < 1 || sampling < 1) return fail(h, UGSM_ERR_INVALID, "bad rows/cols/sampling");
+    if (stride != 4 && stride != 8) return fail(h, UGSM_ERR_INVALID, "point stride must be 4 or 8 floats");
+    if ((reinterpret_cast<uintptr_t>(d_points) & 15) != 0)
+        return fail(h, UGSM_ERR_INVALID, "points not 16-byte aligned");
+    K5Params p;
+    memcpy(p.P1, cam->P1, sizeof p.P1);
+    memcpy(p.P2, cam->P2, sizeof p.P2);
+    p.dX = dX, p.dY = dY, p.pitch = pitch, p.rows = rows, p.cols = cols;
+    p.img = d_img, p.step = step, p.bgr = bgr ? 1 : 0, p.sampling = sampling;
+    p.ncol = div_up(cols, sampling), p.nrow = div_up(rows, sampling);
+    p.points = d_points, p.stride = stride;
+    p.foveated = 0, p.left = p.upper = 0, p.scale = 1.0f;
+    if (src_level >= 0) {
+        if (src_level >= h->cfg.fovea_level)
+            return fail(h, UGSM_ERR_INVALID, "src_level %d outside the stack", src_level);
+        p.foveated = 1;
+        cloud_margins(im_rows, im_cols, h->cfg.fovea_level, src_level, &p.left, &p.upper);
+        // PC:385-388: pow(float, float) is the float overload in C++11 -> libm powf, as on the reference host
+        p.scale = powf((float)1.41421356237309504880, (float)src_level);
+    }
+    int rc = cloud_events(h);
+    if (rc) return rc;
+    dim3 block(K5_T, 8), grid(div_up(p.ncol, K5_T), div_up(p.nrow, K5_T));
+    CK(cudaEventRecord(h->cloud_ev[0], h->stream));
+    k5_cloud<<<grid, block, 0, h->stream>>>(p);
+    CK(cudaEventRecord(h->cloud_ev[1], h->stream));
+    CK(cudaGetLastError());
+    h->launches++;
+    if (npoints) *npoints = (int64_t)p.ncol * p.nrow;
+    return UGSM_OK;
+}
+
+int finish_cloud(ugsm_handle* h) {
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->cloud_ms, h->cloud_ev[0], h->cloud_ev[1]));
+    return UGSM_OK;
 }
 
 }  // namespace
@@ -818,6 +906,9 @@ int ugsm_destroy(ugsm_handle* h) {
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->kev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->cloud_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (h->cloud_buf) cudaFree(h->cloud_buf);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return UGSM_OK;
@@ -955,9 +1046,128 @@ int ugsm_stage_composite(ugsm_handle* h, const float* stackH, const float* stack
     }
     rc = run_composite(h);
     if (rc) return rc;
+    h->last_kind = -1;  // staged planes, no image on the device: nothing for ugsm_cloud_from_match
     float* out[3] = {H, V, C};
     for (int k = 0; k < 3; k++) CK(down2d(out[k], h->comp[0][k], h->lv[0].pitch, h->lv[0].w, h->lv[0].h, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return UGSM_OK;
+}
+
+// ---- point cloud entry points (K5) ----
+int ugsm_cloud_count(int rows, int cols, int sampling, int64_t* npoints) {
+    if (rows < 1 || cols < 1 || sampling < 1 || !npoints) return UGSM_ERR_INVALID;
+    *npoints = (int64_t)div_up(cols, sampling) * div_up(rows, sampling);
+    return UGSM_OK;
+}
+
+int ugsm_cloud_full_device(ugsm_handle* h, const ugsm_camera_pair* cam, const float* dH, const float* dV,
+                           int pitch_floats, int rows, int cols, const uint8_t* d_img, size_t step, int bgr,
+                           int sampling, float* d_points, int point_stride, int64_t* npoints) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (pitch_floats < cols || step < (size_t)cols * 3) return fail(h, UGSM_ERR_INVALID, "bad pitch/step");
+    CK(cudaSetDevice(h->device));
+    int rc = launch_cloud(h, cam, dH, dV, pitch_floats, rows, cols, -1, rows, cols, d_img, step, bgr, sampling,
+                          d_points, point_stride, npoints);
+    if (rc) return rc;
+    return finish_cloud(h);
+}
+
+// Host planes / image / points: staged through one grow-only device buffer.
+static int cloud_host(ugsm_handle* h, const ugsm_camera_pair* cam, const float* X, const float* Y, int rows, int cols,
+                      int src_level, int im_rows, int im_cols, const uint8_t* img, size_t step, int bgr, int sampling,
+                      float* points, int stride, int64_t* npoints) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!cam || !X || !Y || !img || !points) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+    if (rows < 1 || cols < 1 || im_rows < 1 || im_cols < 1 || sampling < 1 || step < (size_t)im_cols * 3)
+        return fail(h, UGSM_ERR_INVALID, "bad rows/cols/step/sampling");
+    if (stride != 4 && stride != 8) return fail(h, UGSM_ERR_INVALID, "point stride must be 4 or 8 floats");
+    CK(cudaSetDevice(h->device));
+    const size_t plane = ((size_t)rows * cols * sizeof(float) + 255) / 256 * 256;
+    const size_t img_bytes = (step * (size_t)im_rows + 255) / 256 * 256;
+    const size_t n = (size_t)div_up(cols, sampling) * div_up(rows, sampling);
+    const size_t pts_bytes = n * stride * sizeof(float);
+    int rc = ensure_cloud_staging(h, 2 * plane + img_bytes + pts_bytes);
+    if (rc) return rc;
+    char* base = static_cast<char*>(h->cloud_buf);
+    float* dX = reinterpret_cast<float*>(base);
+    float* dY = reinterpret_cast<float*>(base + plane);
+    uint8_t* d_img = reinterpret_cast<uint8_t*>(base + 2 * plane);
+    float* d_pts = reinterpret_cast<float*>(base + 2 * plane + img_bytes);
+    CK(cudaMemcpyAsync(dX, X, (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dY, Y, (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_img, img, step * (size_t)im_rows, cudaMemcpyHostToDevice, h->stream));
+    rc = launch_cloud(h, cam, dX, dY, cols, rows, cols, src_level, im_rows, im_cols, d_img, step, bgr, sampling, d_pts,
+                      stride, npoints);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(points, d_pts, pts_bytes, cudaMemcpyDeviceToHost, h->stream));
+    return finish_cloud(h);
+}
+
+int ugsm_cloud_full(ugsm_handle* h, const ugsm_camera_pair* cam, const float* H, const float* V, int rows, int cols,
+                    const uint8_t* img, size_t step, int bgr, int sampling, float* points, int point_stride,
+                    int64_t* npoints) {
+    return cloud_host(h, cam, H, V, rows, cols, -1, rows, cols, img, step, bgr, sampling, points, point_stride,
+                      npoints);
+}
+
+int ugsm_cloud_foveated(ugsm_handle* h, const ugsm_camera_pair* cam, const float* stackH, const float* stackV,
+                        int fov_rows, int fov_cols, int src_level, int im_rows, int im_cols, const uint8_t* img,
+                        size_t step, int bgr, int sampling, float* points, int point_stride, int64_t* npoints) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!stackH || !stackV) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+    if (src_level < 0 || src_level >= h->cfg.fovea_level || fov_rows < 1 || fov_cols < 1)
+        return fail(h, UGSM_ERR_INVALID, "src_level %d outside the stack", src_level);
+    const size_t off = (size_t)src_level * fov_rows * fov_cols;  // PC:900: row yy + fovH * srcLevel
+    return cloud_host(h, cam, stackH + off, stackV + off, fov_rows, fov_cols, src_level, im_rows, im_cols, img, step,
+                      bgr, sampling, points, point_stride, npoints);
+}
+
+int ugsm_cloud_from_match(ugsm_handle* h, const ugsm_camera_pair* cam, int src_level, int sampling, float* points,
+                          int point_stride, int points_on_device, int64_t* npoints) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!cam || !points) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+    if (h->last_kind < 0 || !h->last_rgbL) return fail(h, UGSM_ERR_INVALID, "no match on this handle yet");
+    if (point_stride != 4 && point_stride != 8) return fail(h, UGSM_ERR_INVALID, "point stride must be 4 or 8 floats");
+    if (sampling < 1) return fail(h, UGSM_ERR_INVALID, "bad sampling");
+    CK(cudaSetDevice(h->device));
+    const float *dX, *dY;
+    int pitch, rows, cols, lvl = -1;
+    if (src_level < 0) {
+        if (h->last_kind == 0) {  // full pyramid: level-0 state
+            dX = h->lv[0].st[0], dY = h->lv[0].st[1], pitch = h->lv[0].mpitch;
+        } else if (h->last_kind == 2) {  // hierarchicalDisparity composite
+            dX = h->comp[0][0], dY = h->comp[0][1], pitch = h->lv[0].pitch;
+        } else {
+            return fail(h, UGSM_ERR_INVALID,
+                        "the last match was foveated: pass a stack level (or use ugsm_match_composite)");
+        }
+        rows = h->rows, cols = h->cols;
+    } else {
+        if (h->last_kind == 0) return fail(h, UGSM_ERR_INVALID, "the last match was not foveated");
+        if (src_level >= h->cfg.fovea_level)
+            return fail(h, UGSM_ERR_INVALID, "src_level %d outside the stack", src_level);
+        const LevelBuf& b = h->lv[src_level];
+        dX = b.st[0], dY = b.st[1], pitch = b.mpitch, rows = b.mh, cols = b.mw, lvl = src_level;
+    }
+    const size_t n = (size_t)div_up(cols, sampling) * div_up(rows, sampling);
+    const size_t pts_bytes = n * point_stride * sizeof(float);
+    float* d_pts = points;
+    if (!points_on_device) {
+        int rc = ensure_cloud_staging(h, pts_bytes);
+        if (rc) return rc;
+        d_pts = static_cast<float*>(h->cloud_buf);
+    }
+    // the matcher's input images are RGB8 (UG_GPU_matcher.cpp:513-514)
+    int rc = launch_cloud(h, cam, dX, dY, pitch, rows, cols, lvl, h->rows, h->cols, h->last_rgbL, h->last_step, 0,
+                          sampling, d_pts, point_stride, npoints);
+    if (rc) return rc;
+    if (!points_on_device) CK(cudaMemcpyAsync(points, d_pts, pts_bytes, cudaMemcpyDeviceToHost, h->stream));
+    return finish_cloud(h);
+}
+
+int ugsm_cloud_last_ms(const ugsm_handle* h, float* ms) {
+    if (!h || !ms) return UGSM_ERR_INVALID;
+    *ms = h->cloud_ms;
     return UGSM_OK;
 }
 
