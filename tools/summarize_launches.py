@@ -15,7 +15,7 @@ n = 0
 for r in rd:
     if r["Metric Name"] != "gpu__time_duration.sum":
         continue
-    name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("ugsm::", "")
+    name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("ugsm::", "").replace("void ", "")
     us = float(r["Metric Value"]) / 1e3
     a = agg.setdefault(name, [0, 0.0, 0.0])
     a[0] += 1
