@@ -181,6 +181,9 @@ int ugsm_stage_match_level(ugsm_handle* h, const float* L3, const float* R3, flo
 int ugsm_bench_correlate(ugsm_handle* h, int width, int height, int reps, float* avg_ms);
 int ugsm_bench_smooth(ugsm_handle* h, int width, int height, int passes, int reps, float* avg_ms);
 /* Launch floor of the stream: average time of `reps` back-to-back empty kernel launches. */
+/* K0 timing on synthetic planes: kind 0 = left-energy (dense, 3 planes), 1 = blur + odd-sample decimation
+ * (6 planes), 2 = blur + sqrt2 decimation (6 planes); average launch time over `reps`. */
+int ugsm_bench_pyramid(ugsm_handle* h, int width, int height, int kind, int reps, float* avg_ms);
 int ugsm_bench_null(ugsm_handle* h, int reps, float* avg_ms);
 
 /* ---- row-band execution of the finest levels across GPUs ------------------------

@@ -45,6 +45,32 @@ def test_pyramid_bit_exact(gpu, oracle, capi, shape):
         _assert_same(got[l], want[l], "pyramid level %d of %dx%d" % (l, cols, rows))
 
 
+@pytest.mark.parametrize("shape", [(911, 1203), (1021, 1534), (900, 2050)])
+def test_pyramid_large_planes_bit_exact(gpu, oracle, capi, shape):
+    """Planes above the size where K0 switches to the register-marching kernels (vector loads, running column
+    sums), at widths that are not multiples of 4 / 64 / 128 so that border lanes and partial warps are hit."""
+    rows, cols = shape
+    L, _, _, _ = synth.make_pair(cols, rows, 7)
+    with capi.Handle(levels=6) as h:
+        got = h.stage_pyramid(L)
+    want = oracle.pyramid_rgb(L, 6)
+    for l in range(6):
+        _assert_same(got[l], want[l], "pyramid level %d of %dx%d" % (l, cols, rows))
+
+
+def test_correlate_large_plane_bit_exact(gpu, oracle):
+    """K1 on a 1.1 MP plane: the left-energy planes U come from the dense register-marching K0 kernel."""
+    rows, cols = 911, 1203
+    rng = np.random.default_rng(5)
+    L, R, _, _ = synth.make_pair(cols, rows, 2)
+    L3, R3 = _planes(L), _planes(R)
+    H, V, C = _state(rng, rows, cols)
+    got = gpu.stage_correlate(L3, R3, H, V, C, 0.64, False)
+    want = oracle.correlate(L3, R3, H, V, C, 0.64, False)
+    for g, w, n in zip(got, want, ["Hn", "Vn", "Cn"]):
+        _assert_same(g, w, "correlate %s on %dx%d" % (n, cols, rows))
+
+
 @pytest.mark.parametrize("shape", [(118, 159), (34, 53), (4, 5), (16, 30), (17, 31), (33, 121), (100, 250)])
 @pytest.mark.parametrize("T,first", [(1.0, False), (0.46, False), (1.0, True)])
 def test_correlate_bit_exact(gpu, oracle, shape, T, first):

@@ -26,7 +26,7 @@ SYMBOLS = [
     "ugsm_stage_match_level", "ugsm_bench_correlate", "ugsm_bench_smooth", "ugsm_bench_null", "ugsm_version", "ugsm_band_begin",
     "ugsm_band_level_info", "ugsm_band_iteration", "ugsm_band_upsample", "ugsm_band_emit", "ugsm_band_pack",
     "ugsm_band_unpack", "ugsm_cloud_count", "ugsm_cloud_full", "ugsm_cloud_full_device", "ugsm_cloud_foveated",
-    "ugsm_cloud_from_match", "ugsm_cloud_last_ms",
+    "ugsm_cloud_from_match", "ugsm_cloud_last_ms", "ugsm_bench_pyramid",
 ]
 
 
@@ -146,6 +146,7 @@ def lib():
         L.ugsm_bench_correlate.argtypes = [vp, i, i, i, C.POINTER(C.c_float)]
         L.ugsm_bench_smooth.argtypes = [vp, i, i, i, i, C.POINTER(C.c_float)]
         L.ugsm_bench_null.argtypes = [vp, i, C.POINTER(C.c_float)]
+        L.ugsm_bench_pyramid.argtypes = [vp, i, i, i, i, C.POINTER(C.c_float)]
         L.ugsm_band_begin.argtypes = [vp, vp, vp, i, i, sz, i]
         L.ugsm_band_level_info.argtypes = [vp, i, C.POINTER(BandLevel)]
         L.ugsm_band_iteration.argtypes = [vp, i, i, i, i, i]
@@ -455,6 +456,12 @@ class Handle:
     def bench_null(self, reps=100):
         ms = C.c_float()
         self._ck(lib().ugsm_bench_null(self._h, reps, C.byref(ms)))
+        return ms.value
+
+    def bench_pyramid(self, width, height, kind, reps=10):
+        """kind 0: left energy (dense), 1: blur + odd-sample decimation, 2: blur + sqrt2 decimation."""
+        ms = C.c_float()
+        self._ck(lib().ugsm_bench_pyramid(self._h, width, height, kind, reps, C.byref(ms)))
         return ms.value
 
     def bench_smooth(self, width, height, passes, reps=10):

@@ -82,6 +82,7 @@ struct ugsm_handle {
     int launches = 0;
     bool k_attr_set = false;
     int k1_nw = 2;
+    int k0_rows_dense = 16, k0_rows_dec = 8;  // output rows per warp of k0_march5 (UGSM_K0_ROWS_DENSE / _DEC)
     // CUDA graph of the per-pair launch sequence (pyramid levels .. last level), valid for the current shape
     cudaGraphExec_t graph_exec = nullptr;
     int graph_launches = 0;
@@ -204,6 +205,9 @@ constexpr int K1_TH = 16;
 constexpr int K1S_TH = 8;
 constexpr long K1_SMALL_PIXELS = 400000;  // levels below this use k1_correlate_small
 constexpr long K2_SMALL_PIXELS = 700000;  // levels below this use k2_smooth_box_small
+// K0: the register-marching kernels win on large planes (HBM-bound), the tiled one on small planes (latency-bound)
+constexpr long K0_MARCH_DENSE_PIXELS = 900000;  // output pixels
+constexpr long K0_MARCH_DEC_PIXELS = 200000;
 constexpr int K2_MAX_BH = 72;  // region rows (tile + 2 halos): 2*3*72*128*4 B = 216 KB of shared memory (227 KB max)
 
 size_t k2_smem_bytes(int bh) { return (size_t)2 * 3 * K2_BW * bh * sizeof(float); }
@@ -217,6 +221,8 @@ int set_kernel_attrs(ugsm_handle* h) {
     CK(cudaFuncSetAttribute(k1_correlate<2, K1_TH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     if (const char* e = getenv("UGSM_K1_NW")) h->k1_nw = atoi(e);  // tuning override: warps per K1 CTA (2 or 4)
+    if (const char* e = getenv("UGSM_K0_ROWS_DENSE")) h->k0_rows_dense = atoi(e) > 0 ? atoi(e) : h->k0_rows_dense;
+    if (const char* e = getenv("UGSM_K0_ROWS_DEC")) h->k0_rows_dec = atoi(e) > 0 ? atoi(e) : h->k0_rows_dec;
     CK(cudaFuncSetAttribute(k2_smooth_box, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)k2_smem_bytes(K2_MAX_BH)));
     h->k_attr_set = true;
@@ -295,6 +301,14 @@ void launch_k3(ugsm_handle* h, float* const src[3], int w, int hh, int spitch, i
     h->launches++;
 }
 
+// The register-marching K0 kernels use aligned vector accesses.
+bool planes_aligned(const K0Planes& pl, int n, int spitch, int dpitch) {
+    if ((spitch & 3) || (dpitch & 3)) return false;
+    for (int k = 0; k < n; k++)
+        if ((reinterpret_cast<uintptr_t>(pl.src[k]) & 15) || (reinterpret_cast<uintptr_t>(pl.dst[k]) & 15)) return false;
+    return true;
+}
+
 // U = colT(rowT(L^2)) for `n` planes of equal dims in one launch.
 void launch_energy(ugsm_handle* h, const float* const* L, float* const* U, int n, int w, int hh, int pitch) {
     K0Planes pl;
@@ -302,8 +316,14 @@ void launch_energy(ugsm_handle* h, const float* const* L, float* const* U, int n
         pl.src[k] = L[k < n ? k : 0];
         pl.dst[k] = U[k < n ? k : 0];
     }
-    dim3 grid(div_up(w, 32), div_up(hh, 32), n);
-    k0_sep5<0, true, true><<<grid, 256, 0, h->stream>>>(pl, w, hh, pitch, w, hh, pitch, 1.0f, h->taps);
+    if ((long)w * hh >= K0_MARCH_DENSE_PIXELS && planes_aligned(pl, n, pitch, pitch)) {
+        const int rpw = h->k0_rows_dense;
+        dim3 grid(div_up(w, 128), div_up(hh, 8 * rpw), n);
+        k0_march5<0, true, true><<<grid, dim3(32, 8), 0, h->stream>>>(pl, w, hh, pitch, w, hh, pitch, rpw, h->taps);
+    } else {
+        dim3 grid(div_up(w, 32), div_up(hh, 32), n);
+        k0_sep5<0, true, true><<<grid, 256, 0, h->stream>>>(pl, w, hh, pitch, w, hh, pitch, 1.0f, h->taps);
+    }
     h->launches++;
 }
 
@@ -325,6 +345,12 @@ void launch_blur_decimate(ugsm_handle* h, int mode, const float* const* src, flo
     if (mode == 0) {
         float s = SCALE_D;  // MGL:1083
         k0_sep5<2, false, false><<<grid, 256, 0, h->stream>>>(pl, w, hh, spitch, w2, h2, dpitch, s, h->taps);
+    } else if ((long)w2 * h2 >= K0_MARCH_DEC_PIXELS && planes_aligned(pl, n, spitch, dpitch)) {
+        // scalefactors = (int)(SCALE*SCALE + .5) = 2 (MGL:1090): the odd samples (2x+1, 2y+1)
+        const int rpw = h->k0_rows_dec;
+        dim3 mgrid(div_up(w2, 64), div_up(h2, 8 * rpw), n);
+        k0_march5<1, false, false><<<mgrid, dim3(32, 8), 0, h->stream>>>(pl, w, hh, spitch, w2, h2, dpitch, rpw,
+                                                                          h->taps);
     } else {
         float s = 0.000 + (int)(SCALE_D * SCALE_D + 0.5);  // MGL:1090
         k0_sep5<1, false, false><<<grid, 256, 0, h->stream>>>(pl, w, hh, spitch, w2, h2, dpitch, s, h->taps);
@@ -1654,6 +1680,50 @@ int ugsm_stage_poly(ugsm_handle* h, const float* l, const float* c, const float*
 }
 
 __global__ void k_null(int) {}
+
+/* K0 timing: kind 0 = left-energy (dense, 3 planes), 1 = blur + odd-sample decimation (6 planes), 2 = blur +
+ * sqrt2 decimation (6 planes) of width x height planes; average of `reps` launches. */
+int ugsm_bench_pyramid(ugsm_handle* h, int width, int height, int kind, int reps, float* avg_ms) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (width < 8 || height < 8 || reps < 1 || kind < 0 || kind > 2 || !avg_ms)
+        return fail(h, UGSM_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(h->device));
+    int rc = set_kernel_attrs(h);
+    if (rc) return rc;
+    const int n = kind == 0 ? 3 : 6;
+    const int w2 = kind == 0 ? width : (kind == 1 ? (int)((int)(width / SCALE_D) / SCALE_D) : (int)(width / SCALE_D));
+    const int h2 = kind == 0 ? height : (kind == 1 ? (int)((int)(height / SCALE_D) / SCALE_D) : (int)(height / SCALE_D));
+    const int sp = align_up(width, 32), dp = align_up(w2, 32);
+    TmpDev tmp;
+    const float* src[6];
+    float* dst[6];
+    for (int k = 0; k < n; k++) {
+        float* s = tmp.alloc<float>((size_t)sp * height);
+        dst[k] = tmp.alloc<float>((size_t)dp * h2);
+        if (!s || !dst[k]) return fail(h, UGSM_ERR_NOMEM, "bench allocation failed");
+        k_fill_synth<<<div_up(sp * height, 256), 256, 0, h->stream>>>(s, (size_t)sp * height, 16.f, 240.f, 17u * k + 1);
+        src[k] = s;
+    }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < reps + 2; i++) {
+        if (i == 2) CK(cudaEventRecord(e0, h->stream));
+        if (kind == 0)
+            launch_energy(h, src, dst, n, width, height, sp);
+        else
+            launch_blur_decimate(h, kind == 2 ? 0 : 1, src, dst, n, width, height, sp, w2, h2, dp);
+    }
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaGetLastError());
+    *avg_ms = ms / reps;
+    return UGSM_OK;
+}
 
 /* Launch floor: average time of `reps` back-to-back empty launches on the handle's stream. */
 int ugsm_bench_null(ugsm_handle* h, int reps, float* avg_ms) {
