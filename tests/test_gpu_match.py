@@ -195,3 +195,33 @@ def test_16mp_full_and_foveated_bit_exact(capi, oracle):
     wH, wV, wC, fw, fh = oracle.match_foveated(L, R)
     assert (fw, fh) == (615, 407) == (fov[3], fov[4]) and fov[0].shape == (7 * 407, 615)
     _cmp(fov[:3], (wH, wV, wC), "16MP foveated")
+
+
+def test_pageable_staging_equals_plain_path(capi, monkeypatch):
+    """Pageable host buffers of >= 8 MB go through pinned staging with copy threads (what a caller of the
+    MatchGPULib facade gets): same bits as the plain cudaMemcpy path, with fresh and with reused output planes,
+    also for the foveated stack (too small to be staged on the way out) and for padded rows."""
+    L, R, _, _ = synth.make_pair(2048, 1536, 11)
+    Lp = np.zeros((1536, 2048 * 3 + 64), np.uint8)
+    Rp = np.zeros_like(Lp)
+    Lp[:, :2048 * 3] = L.reshape(1536, -1)
+    Rp[:, :2048 * 3] = R.reshape(1536, -1)
+    Lv = np.lib.stride_tricks.as_strided(Lp, shape=(1536, 2048, 3), strides=(Lp.strides[0], 3, 1))
+    Rv = np.lib.stride_tricks.as_strided(Rp, shape=(1536, 2048, 3), strides=(Rp.strides[0], 3, 1))
+    monkeypatch.setenv("UGSM_HOST_THREADS", "0")
+    with capi.Handle(levels=8) as h:
+        want = h.match_full(L, R)
+        want_stack = h.match_foveated(L, R)[:3]
+    for threads in ("3", "8"):
+        monkeypatch.setenv("UGSM_HOST_THREADS", threads)
+        with capi.Handle(levels=8) as h:
+            got = h.match_full(L, R)
+            again = h.match_full(L, R, out=tuple(np.full_like(g, np.nan) for g in got))
+            stack = h.match_foveated(L, R)[:3]
+            outs = tuple(np.empty((1536, 2048), np.float32) for _ in range(3))
+            h._ck(capi.lib().ugsm_match_full(h._h, Lv.ctypes.data_as(capi.C.c_void_p), Rv.ctypes.data_as(capi.C.c_void_p),
+                                             1536, 2048, Lp.strides[0], *[o.ctypes.data_as(capi.C.c_void_p) for o in outs]))
+        for a, b, c, d in zip(got, again, outs, want):
+            assert np.array_equal(a, d) and np.array_equal(b, d) and np.array_equal(c, d)
+        for a, d in zip(stack, want_stack):
+            assert np.array_equal(a, d)

@@ -19,7 +19,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ugsm_kernels.cuh"
@@ -98,6 +102,13 @@ struct ugsm_handle {
     int last_kind = -1;  // 0 full, 1 foveated, 2 foveated + composite
     void* cloud_buf = nullptr;
     size_t cloud_bytes = 0;
+    // pageable host buffers (malloc'd planes of the reference API): pinned staging + copy threads
+    int host_threads = 8;  // UGSM_HOST_THREADS; < 2 = plain cudaMemcpyAsync from/to the caller's memory
+    uint8_t* pin_in[2] = {nullptr, nullptr};
+    size_t pin_in_bytes = 0;
+    float* pin_out[3] = {nullptr, nullptr, nullptr};
+    size_t pin_out_floats = 0;
+    std::vector<cudaEvent_t> chunk_ev;
     cudaEvent_t cloud_ev[2] = {};
     float cloud_ms = 0.f;
 };
@@ -840,6 +851,133 @@ int finish_cloud(ugsm_handle* h) {
     return UGSM_OK;
 }
 
+// ---- pageable host buffers -------------------------------------------------------------------------
+// The reference API hands out malloc'd planes (MGL:372-399: the node frees them), i.e. pageable memory:
+// a plain cudaMemcpy of 96 MB in + 193 MB out costs ~50 ms at 16 MP, most of it first-touch page faults
+// and the driver's single-threaded staging.  Pageable buffers therefore go through pinned staging
+// buffers in chunks, with a few copy threads on the host side: user -> pinned copies run ahead of the
+// H2D DMA; the output pages are pre-faulted while the GPU computes, and pinned -> user copies follow
+// the D2H DMA chunk by chunk.
+constexpr size_t HOST_CHUNK = (size_t)4 << 20;
+
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int ensure_pinned(ugsm_handle* h, size_t rgb_bytes, size_t out_floats) {
+    if (rgb_bytes > h->pin_in_bytes) {
+        for (int k = 0; k < 2; k++) {
+            if (h->pin_in[k]) cudaFreeHost(h->pin_in[k]);
+            h->pin_in[k] = nullptr;
+        }
+        h->pin_in_bytes = 0;
+        for (int k = 0; k < 2; k++) CK(cudaHostAlloc((void**)&h->pin_in[k], rgb_bytes, cudaHostAllocDefault));
+        h->pin_in_bytes = rgb_bytes;
+    }
+    if (out_floats > h->pin_out_floats) {
+        for (int k = 0; k < 3; k++) {
+            if (h->pin_out[k]) cudaFreeHost(h->pin_out[k]);
+            h->pin_out[k] = nullptr;
+        }
+        h->pin_out_floats = 0;
+        for (int k = 0; k < 3; k++)
+            CK(cudaHostAlloc((void**)&h->pin_out[k], out_floats * sizeof(float), cudaHostAllocDefault));
+        h->pin_out_floats = out_floats;
+    }
+    return UGSM_OK;
+}
+
+// user (pageable) -> pinned -> device, both images.  Copy threads fill chunks in any order; the calling
+// thread enqueues the DMA of a chunk as soon as it is filled, in order.
+int staged_h2d(ugsm_handle* h, const uint8_t* const src[2], size_t bytes) {
+    const int nch = (int)((bytes + HOST_CHUNK - 1) / HOST_CHUNK), total = 2 * nch;
+    std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[total]);
+    for (int c = 0; c < total; c++) done[c].store(0, std::memory_order_relaxed);
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int c = next.fetch_add(1);
+            if (c >= total) break;
+            const int img = c / nch;
+            const size_t off = (size_t)(c % nch) * HOST_CHUNK, len = std::min(HOST_CHUNK, bytes - off);
+            memcpy(h->pin_in[img] + off, src[img] + off, len);
+            done[c].store(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < h->host_threads; t++) pool.emplace_back(work);
+    cudaError_t err = cudaSuccess;
+    for (int c = 0; c < total; c++) {
+        while (!done[c].load(std::memory_order_acquire)) std::this_thread::yield();
+        const int img = c / nch;
+        const size_t off = (size_t)(c % nch) * HOST_CHUNK, len = std::min(HOST_CHUNK, bytes - off);
+        if (err == cudaSuccess)
+            err = cudaMemcpyAsync(h->d_rgb[img] + off, h->pin_in[img] + off, len, cudaMemcpyHostToDevice, h->stream);
+    }
+    for (auto& t : pool) t.join();
+    if (err != cudaSuccess) return fail(h, UGSM_ERR_CUDA, "staged H2D failed: %s", cudaGetErrorString(err));
+    return UGSM_OK;
+}
+
+// device -> pinned -> user (pageable), three planes of `floats` each.  Called right after the kernels
+// of the pair were enqueued: the copy threads first pre-fault the caller's pages (while the GPU is
+// busy), then follow the D2H DMA chunk by chunk.
+int staged_d2h(ugsm_handle* h, float* const dst[3], size_t floats) {
+    const size_t bytes = floats * sizeof(float);
+    const int nch = (int)((bytes + HOST_CHUNK - 1) / HOST_CHUNK), total = 3 * nch;
+    while ((int)h->chunk_ev.size() < total) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->chunk_ev.push_back(ev);
+    }
+    for (int c = 0; c < total; c++) {
+        const int k = c / nch;
+        const size_t off = (size_t)(c % nch) * HOST_CHUNK, len = std::min(HOST_CHUNK, bytes - off);
+        CK(cudaMemcpyAsync((char*)h->pin_out[k] + off, (const char*)h->d_out[k] + off, len, cudaMemcpyDeviceToHost,
+                           h->stream));
+        CK(cudaEventRecord(h->chunk_ev[c], h->stream));
+    }
+    std::atomic<int> next_touch(0), next(0), touch_done(0);
+    std::atomic<int> failed(0);
+    const int nthreads = h->host_threads;
+    const int device = h->device;
+    auto work = [&]() {
+        cudaSetDevice(device);
+        for (;;) {  // first touch of the output pages, one write per 4 KB page
+            const int c = next_touch.fetch_add(1);
+            if (c >= total) break;
+            const int k = c / nch;
+            const size_t off = (size_t)(c % nch) * HOST_CHUNK, len = std::min(HOST_CHUNK, bytes - off);
+            volatile char* p = (volatile char*)dst[k] + off;
+            for (size_t i = 0; i < len; i += 4096) p[i] = 0;
+        }
+        // no thread may write results before every thread has stopped writing zeros
+        touch_done.fetch_add(1, std::memory_order_acq_rel);
+        while (touch_done.load(std::memory_order_acquire) < nthreads) std::this_thread::yield();
+        for (;;) {
+            const int c = next.fetch_add(1);
+            if (c >= total) break;
+            const int k = c / nch;
+            const size_t off = (size_t)(c % nch) * HOST_CHUNK, len = std::min(HOST_CHUNK, bytes - off);
+            if (cudaEventSynchronize(h->chunk_ev[c]) != cudaSuccess) {
+                failed.store(1);
+                break;
+            }
+            memcpy((char*)dst[k] + off, (const char*)h->pin_out[k] + off, len);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+    if (failed.load()) return fail(h, UGSM_ERR_CUDA, "staged D2H failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return UGSM_OK;
+}
+
 }  // namespace
 
 // =============================================================================== C-ABI
@@ -935,6 +1073,12 @@ int ugsm_destroy(ugsm_handle* h) {
     for (auto& ev : h->cloud_ev)
         if (ev) cudaEventDestroy(ev);
     if (h->cloud_buf) cudaFree(h->cloud_buf);
+    for (int k = 0; k < 2; k++)
+        if (h->pin_in[k]) cudaFreeHost(h->pin_in[k]);
+    for (int k = 0; k < 3; k++)
+        if (h->pin_out[k]) cudaFreeHost(h->pin_out[k]);
+    for (auto& ev : h->chunk_ev)
+        if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return UGSM_OK;
@@ -995,9 +1139,24 @@ static int match_host(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, 
     size_t out_floats = (mode == 0 || composite) ? (size_t)rows * cols : (size_t)d.stack_rows * d.fov_width;
     rc = ensure_staging(h, rgb_bytes, out_floats);
     if (rc) return rc;
+    if (const char* e = getenv("UGSM_HOST_THREADS")) h->host_threads = std::min(64, atoi(e));  // tuning override
+    const bool big = rgb_bytes >= 2 * HOST_CHUNK && h->host_threads >= 2;
+    const bool stage_in = big && is_pageable(rgbL) && is_pageable(rgbR);
+    const bool stage_out = big && out_floats * sizeof(float) >= 2 * HOST_CHUNK && is_pageable(o0) && is_pageable(o1) &&
+                           is_pageable(o2);
+    if (stage_in || stage_out) {
+        rc = ensure_pinned(h, stage_in ? rgb_bytes : 0, stage_out ? out_floats : 0);
+        if (rc) return rc;
+    }
     CK(cudaEventRecord(h->ev[3], h->stream));
-    CK(cudaMemcpyAsync(h->d_rgb[0], rgbL, rgb_bytes, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_rgb[1], rgbR, rgb_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (stage_in) {
+        const uint8_t* const src[2] = {rgbL, rgbR};
+        rc = staged_h2d(h, src, rgb_bytes);
+        if (rc) return rc;
+    } else {
+        CK(cudaMemcpyAsync(h->d_rgb[0], rgbL, rgb_bytes, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_rgb[1], rgbR, rgb_bytes, cudaMemcpyHostToDevice, h->stream));
+    }
     rc = run_pair(h, h->d_rgb[0], h->d_rgb[1], rows, cols, step, mode);
     if (rc) return rc;
     if (composite) {
@@ -1011,8 +1170,13 @@ static int match_host(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, 
     }
     if (rc) return rc;
     float* outs[3] = {o0, o1, o2};
-    for (int k = 0; k < 3; k++)
-        CK(cudaMemcpyAsync(outs[k], h->d_out[k], out_floats * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (stage_out) {
+        rc = staged_d2h(h, outs, out_floats);
+        if (rc) return rc;
+    } else {
+        for (int k = 0; k < 3; k++)
+            CK(cudaMemcpyAsync(outs[k], h->d_out[k], out_floats * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     rc = finish_timing(h);
     if (rc) return rc;
