@@ -116,7 +116,7 @@ def cpu_sample(target_seconds=20.0):
     import ugsm_oracle as oracle
     from ug_stereomatcher_b200 import synth
 
-    cores = oracle.num_threads()
+    cores = oracle.use_all_host_cores()
     # calibrate on 640x480 (2.48 M pixel-iterations), then pick the largest sample that fits the budget
     L, R, _, _ = synth.make_pair(640, 480, 0)
     oracle.match_full(L[:64, :64].copy(), R[:64, :64].copy(), oracle.default_config(levels=3))  # spin up OpenMP

@@ -37,6 +37,15 @@ void ugsmo_config_default(ugsmo_config* cfg) {
     cfg->max_iters = 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms of bench.py ask for the host cores explicitly */
+void ugsmo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int ugsmo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

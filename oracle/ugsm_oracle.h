@@ -47,6 +47,7 @@ typedef struct ugsmo_config {
 } ugsmo_config;
 
 void ugsmo_config_default(ugsmo_config* cfg);
+void ugsmo_set_num_threads(int n);
 int ugsmo_num_threads(void);
 
 /* MatchGPULib.cpp:735-775 / 344-348 */

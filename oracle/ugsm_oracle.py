@@ -56,6 +56,20 @@ def num_threads():
     return lib().ugsmo_num_threads()
 
 
+def set_num_threads(n):
+    lib().ugsmo_set_num_threads(int(n))
+
+
+def use_all_host_cores():
+    """OpenMP threads = the cores this process may run on (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    set_num_threads(n)
+    return num_threads()
+
+
 def _f(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
