@@ -12,7 +12,7 @@ from ug_stereomatcher_b200 import capi, synth
 
 L, R, _, _ = synth.make_pair(4928, 3264, 0)
 ref = None
-for threads in (0, 2, 4, 8, 16):
+for threads in (0, 4, 8):
     os.environ["UGSM_HOST_THREADS"] = str(threads)
     with capi.Handle() as h:
         fresh, reuse = [], []

@@ -104,10 +104,10 @@ struct ugsm_handle {
     size_t cloud_bytes = 0;
     // pageable host buffers (malloc'd planes of the reference API): pinned staging + copy threads
     int host_threads = 8;  // UGSM_HOST_THREADS; < 2 = plain cudaMemcpyAsync from/to the caller's memory
-    uint8_t* pin_in[2] = {nullptr, nullptr};
+    char* pin_in = nullptr;
     size_t pin_in_bytes = 0;
-    float* pin_out[3] = {nullptr, nullptr, nullptr};
-    size_t pin_out_floats = 0;
+    char* pin_out = nullptr;
+    size_t pin_out_bytes = 0;
     std::vector<cudaEvent_t> chunk_ev;
     cudaEvent_t cloud_ev[2] = {};
     float cloud_ms = 0.f;
@@ -869,33 +869,58 @@ bool is_pageable(const void* p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
-int ensure_pinned(ugsm_handle* h, size_t rgb_bytes, size_t out_floats) {
-    if (rgb_bytes > h->pin_in_bytes) {
-        for (int k = 0; k < 2; k++) {
-            if (h->pin_in[k]) cudaFreeHost(h->pin_in[k]);
-            h->pin_in[k] = nullptr;
-        }
+struct HostXfer {  // one buffer of a staged transfer
+    const void* src;  // H2D: caller's memory; D2H: device memory
+    void* dst;        // H2D: device memory;   D2H: caller's memory
+    size_t bytes;
+};
+struct HostChunk {
+    const char* src;
+    char* dst;
+    char* pin;
+    size_t len;
+};
+
+int ensure_pinned(ugsm_handle* h, size_t in_bytes, size_t out_bytes) {
+    if (in_bytes > h->pin_in_bytes) {
+        if (h->pin_in) cudaFreeHost(h->pin_in);
+        h->pin_in = nullptr;
         h->pin_in_bytes = 0;
-        for (int k = 0; k < 2; k++) CK(cudaHostAlloc((void**)&h->pin_in[k], rgb_bytes, cudaHostAllocDefault));
-        h->pin_in_bytes = rgb_bytes;
+        CK(cudaHostAlloc((void**)&h->pin_in, in_bytes, cudaHostAllocDefault));
+        h->pin_in_bytes = in_bytes;
     }
-    if (out_floats > h->pin_out_floats) {
-        for (int k = 0; k < 3; k++) {
-            if (h->pin_out[k]) cudaFreeHost(h->pin_out[k]);
-            h->pin_out[k] = nullptr;
-        }
-        h->pin_out_floats = 0;
-        for (int k = 0; k < 3; k++)
-            CK(cudaHostAlloc((void**)&h->pin_out[k], out_floats * sizeof(float), cudaHostAllocDefault));
-        h->pin_out_floats = out_floats;
+    if (out_bytes > h->pin_out_bytes) {
+        if (h->pin_out) cudaFreeHost(h->pin_out);
+        h->pin_out = nullptr;
+        h->pin_out_bytes = 0;
+        CK(cudaHostAlloc((void**)&h->pin_out, out_bytes, cudaHostAllocDefault));
+        h->pin_out_bytes = out_bytes;
     }
     return UGSM_OK;
 }
 
-// user (pageable) -> pinned -> device, both images.  Copy threads fill chunks in any order; the calling
-// thread enqueues the DMA of a chunk as soon as it is filled, in order.
-int staged_h2d(ugsm_handle* h, const uint8_t* const src[2], size_t bytes) {
-    const int nch = (int)((bytes + HOST_CHUNK - 1) / HOST_CHUNK), total = 2 * nch;
+size_t staged_bytes(const HostXfer* x, int n) {
+    size_t t = 0;
+    for (int i = 0; i < n; i++) t += (x[i].bytes + 255) / 256 * 256;
+    return t;
+}
+
+std::vector<HostChunk> make_chunks(const HostXfer* x, int n, char* pinned) {
+    std::vector<HostChunk> ch;
+    for (int i = 0; i < n; i++) {
+        for (size_t off = 0; off < x[i].bytes; off += HOST_CHUNK)
+            ch.push_back({(const char*)x[i].src + off, (char*)x[i].dst + off, pinned + off,
+                          std::min(HOST_CHUNK, x[i].bytes - off)});
+        pinned += (x[i].bytes + 255) / 256 * 256;
+    }
+    return ch;
+}
+
+// caller (pageable) -> pinned -> device.  Copy threads fill chunks in any order; the calling thread enqueues
+// the DMA of a chunk as soon as it is filled, in order.
+int staged_h2d(ugsm_handle* h, const HostXfer* x, int n) {
+    const std::vector<HostChunk> ch = make_chunks(x, n, h->pin_in);
+    const int total = (int)ch.size();
     std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[total]);
     for (int c = 0; c < total; c++) done[c].store(0, std::memory_order_relaxed);
     std::atomic<int> next(0);
@@ -903,9 +928,7 @@ int staged_h2d(ugsm_handle* h, const uint8_t* const src[2], size_t bytes) {
         for (;;) {
             const int c = next.fetch_add(1);
             if (c >= total) break;
-            const int img = c / nch;
-            const size_t off = (size_t)(c % nch) * HOST_CHUNK, len = std::min(HOST_CHUNK, bytes - off);
-            memcpy(h->pin_in[img] + off, src[img] + off, len);
+            memcpy(ch[c].pin, ch[c].src, ch[c].len);
             done[c].store(1, std::memory_order_release);
         }
     };
@@ -914,32 +937,25 @@ int staged_h2d(ugsm_handle* h, const uint8_t* const src[2], size_t bytes) {
     cudaError_t err = cudaSuccess;
     for (int c = 0; c < total; c++) {
         while (!done[c].load(std::memory_order_acquire)) std::this_thread::yield();
-        const int img = c / nch;
-        const size_t off = (size_t)(c % nch) * HOST_CHUNK, len = std::min(HOST_CHUNK, bytes - off);
-        if (err == cudaSuccess)
-            err = cudaMemcpyAsync(h->d_rgb[img] + off, h->pin_in[img] + off, len, cudaMemcpyHostToDevice, h->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(ch[c].dst, ch[c].pin, ch[c].len, cudaMemcpyHostToDevice, h->stream);
     }
     for (auto& t : pool) t.join();
     if (err != cudaSuccess) return fail(h, UGSM_ERR_CUDA, "staged H2D failed: %s", cudaGetErrorString(err));
     return UGSM_OK;
 }
 
-// device -> pinned -> user (pageable), three planes of `floats` each.  Called right after the kernels
-// of the pair were enqueued: the copy threads first pre-fault the caller's pages (while the GPU is
-// busy), then follow the D2H DMA chunk by chunk.
-int staged_d2h(ugsm_handle* h, float* const dst[3], size_t floats) {
-    const size_t bytes = floats * sizeof(float);
-    const int nch = (int)((bytes + HOST_CHUNK - 1) / HOST_CHUNK), total = 3 * nch;
+// device -> pinned -> caller (pageable).  Called right after the producing kernels were enqueued: the copy
+// threads first pre-fault the caller's pages (while the GPU is busy), then follow the D2H DMA chunk by chunk.
+int staged_d2h(ugsm_handle* h, const HostXfer* x, int n) {
+    const std::vector<HostChunk> ch = make_chunks(x, n, h->pin_out);
+    const int total = (int)ch.size();
     while ((int)h->chunk_ev.size() < total) {
         cudaEvent_t ev;
         CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         h->chunk_ev.push_back(ev);
     }
     for (int c = 0; c < total; c++) {
-        const int k = c / nch;
-        const size_t off = (size_t)(c % nch) * HOST_CHUNK, len = std::min(HOST_CHUNK, bytes - off);
-        CK(cudaMemcpyAsync((char*)h->pin_out[k] + off, (const char*)h->d_out[k] + off, len, cudaMemcpyDeviceToHost,
-                           h->stream));
+        CK(cudaMemcpyAsync(ch[c].pin, ch[c].src, ch[c].len, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaEventRecord(h->chunk_ev[c], h->stream));
     }
     std::atomic<int> next_touch(0), next(0), touch_done(0);
@@ -951,10 +967,8 @@ int staged_d2h(ugsm_handle* h, float* const dst[3], size_t floats) {
         for (;;) {  // first touch of the output pages, one write per 4 KB page
             const int c = next_touch.fetch_add(1);
             if (c >= total) break;
-            const int k = c / nch;
-            const size_t off = (size_t)(c % nch) * HOST_CHUNK, len = std::min(HOST_CHUNK, bytes - off);
-            volatile char* p = (volatile char*)dst[k] + off;
-            for (size_t i = 0; i < len; i += 4096) p[i] = 0;
+            volatile char* p = ch[c].dst;
+            for (size_t i = 0; i < ch[c].len; i += 4096) p[i] = 0;
         }
         // no thread may write results before every thread has stopped writing zeros
         touch_done.fetch_add(1, std::memory_order_acq_rel);
@@ -962,13 +976,11 @@ int staged_d2h(ugsm_handle* h, float* const dst[3], size_t floats) {
         for (;;) {
             const int c = next.fetch_add(1);
             if (c >= total) break;
-            const int k = c / nch;
-            const size_t off = (size_t)(c % nch) * HOST_CHUNK, len = std::min(HOST_CHUNK, bytes - off);
             if (cudaEventSynchronize(h->chunk_ev[c]) != cudaSuccess) {
                 failed.store(1);
                 break;
             }
-            memcpy((char*)dst[k] + off, (const char*)h->pin_out[k] + off, len);
+            memcpy(ch[c].dst, ch[c].pin, ch[c].len);
         }
     };
     std::vector<std::thread> pool;
@@ -976,6 +988,18 @@ int staged_d2h(ugsm_handle* h, float* const dst[3], size_t floats) {
     for (auto& t : pool) t.join();
     if (failed.load()) return fail(h, UGSM_ERR_CUDA, "staged D2H failed: %s", cudaGetErrorString(cudaGetLastError()));
     return UGSM_OK;
+}
+
+// Are these host buffers worth staging?  (all pageable, big enough, copy threads enabled)
+bool want_staging(ugsm_handle* h, const HostXfer* x, int n, bool host_is_src) {
+    if (const char* e = getenv("UGSM_HOST_THREADS")) h->host_threads = std::min(64, atoi(e));  // tuning override
+    if (h->host_threads < 2) return false;
+    size_t total = 0;
+    for (int i = 0; i < n; i++) {
+        total += x[i].bytes;
+        if (!is_pageable(host_is_src ? x[i].src : x[i].dst)) return false;
+    }
+    return total >= 4 * HOST_CHUNK;
 }
 
 }  // namespace
@@ -1073,10 +1097,8 @@ int ugsm_destroy(ugsm_handle* h) {
     for (auto& ev : h->cloud_ev)
         if (ev) cudaEventDestroy(ev);
     if (h->cloud_buf) cudaFree(h->cloud_buf);
-    for (int k = 0; k < 2; k++)
-        if (h->pin_in[k]) cudaFreeHost(h->pin_in[k]);
-    for (int k = 0; k < 3; k++)
-        if (h->pin_out[k]) cudaFreeHost(h->pin_out[k]);
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
     for (auto& ev : h->chunk_ev)
         if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1139,19 +1161,19 @@ static int match_host(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, 
     size_t out_floats = (mode == 0 || composite) ? (size_t)rows * cols : (size_t)d.stack_rows * d.fov_width;
     rc = ensure_staging(h, rgb_bytes, out_floats);
     if (rc) return rc;
-    if (const char* e = getenv("UGSM_HOST_THREADS")) h->host_threads = std::min(64, atoi(e));  // tuning override
-    const bool big = rgb_bytes >= 2 * HOST_CHUNK && h->host_threads >= 2;
-    const bool stage_in = big && is_pageable(rgbL) && is_pageable(rgbR);
-    const bool stage_out = big && out_floats * sizeof(float) >= 2 * HOST_CHUNK && is_pageable(o0) && is_pageable(o1) &&
-                           is_pageable(o2);
+    float* outs[3] = {o0, o1, o2};
+    const HostXfer xin[2] = {{rgbL, h->d_rgb[0], rgb_bytes}, {rgbR, h->d_rgb[1], rgb_bytes}};
+    const HostXfer xout[3] = {{h->d_out[0], o0, out_floats * sizeof(float)},
+                              {h->d_out[1], o1, out_floats * sizeof(float)},
+                              {h->d_out[2], o2, out_floats * sizeof(float)}};
+    const bool stage_in = want_staging(h, xin, 2, true), stage_out = want_staging(h, xout, 3, false);
     if (stage_in || stage_out) {
-        rc = ensure_pinned(h, stage_in ? rgb_bytes : 0, stage_out ? out_floats : 0);
+        rc = ensure_pinned(h, stage_in ? staged_bytes(xin, 2) : 0, stage_out ? staged_bytes(xout, 3) : 0);
         if (rc) return rc;
     }
     CK(cudaEventRecord(h->ev[3], h->stream));
     if (stage_in) {
-        const uint8_t* const src[2] = {rgbL, rgbR};
-        rc = staged_h2d(h, src, rgb_bytes);
+        rc = staged_h2d(h, xin, 2);
         if (rc) return rc;
     } else {
         CK(cudaMemcpyAsync(h->d_rgb[0], rgbL, rgb_bytes, cudaMemcpyHostToDevice, h->stream));
@@ -1169,9 +1191,8 @@ static int match_host(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, 
                        : emit_stack(h, h->d_out[0], h->d_out[1], h->d_out[2]);
     }
     if (rc) return rc;
-    float* outs[3] = {o0, o1, o2};
     if (stage_out) {
-        rc = staged_d2h(h, outs, out_floats);
+        rc = staged_d2h(h, xout, 3);
         if (rc) return rc;
     } else {
         for (int k = 0; k < 3; k++)
@@ -1283,13 +1304,29 @@ static int cloud_host(ugsm_handle* h, const ugsm_camera_pair* cam, const float* 
     float* dY = reinterpret_cast<float*>(base + plane);
     uint8_t* d_img = reinterpret_cast<uint8_t*>(base + 2 * plane);
     float* d_pts = reinterpret_cast<float*>(base + 2 * plane + img_bytes);
-    CK(cudaMemcpyAsync(dX, X, (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(dY, Y, (size_t)rows * cols * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(d_img, img, step * (size_t)im_rows, cudaMemcpyHostToDevice, h->stream));
+    const size_t plane_bytes = (size_t)rows * cols * sizeof(float);
+    const HostXfer xin[3] = {{X, dX, plane_bytes}, {Y, dY, plane_bytes}, {img, d_img, step * (size_t)im_rows}};
+    const HostXfer xout[1] = {{d_pts, points, pts_bytes}};
+    const bool stage_in = want_staging(h, xin, 3, true), stage_out = want_staging(h, xout, 1, false);
+    if (stage_in || stage_out) {
+        rc = ensure_pinned(h, stage_in ? staged_bytes(xin, 3) : 0, stage_out ? staged_bytes(xout, 1) : 0);
+        if (rc) return rc;
+    }
+    if (stage_in) {
+        rc = staged_h2d(h, xin, 3);
+        if (rc) return rc;
+    } else {
+        for (int k = 0; k < 3; k++) CK(cudaMemcpyAsync(xin[k].dst, xin[k].src, xin[k].bytes, cudaMemcpyHostToDevice, h->stream));
+    }
     rc = launch_cloud(h, cam, dX, dY, cols, rows, cols, src_level, im_rows, im_cols, d_img, step, bgr, sampling, d_pts,
                       stride, npoints);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(points, d_pts, pts_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (stage_out) {
+        rc = staged_d2h(h, xout, 1);
+        if (rc) return rc;
+    } else {
+        CK(cudaMemcpyAsync(points, d_pts, pts_bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
     return finish_cloud(h);
 }
 
@@ -1351,7 +1388,17 @@ int ugsm_cloud_from_match(ugsm_handle* h, const ugsm_camera_pair* cam, int src_l
     int rc = launch_cloud(h, cam, dX, dY, pitch, rows, cols, lvl, h->rows, h->cols, h->last_rgbL, h->last_step, 0,
                           sampling, d_pts, point_stride, npoints);
     if (rc) return rc;
-    if (!points_on_device) CK(cudaMemcpyAsync(points, d_pts, pts_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (!points_on_device) {
+        const HostXfer xout[1] = {{d_pts, points, pts_bytes}};
+        if (want_staging(h, xout, 1, false)) {
+            rc = ensure_pinned(h, 0, staged_bytes(xout, 1));
+            if (rc) return rc;
+            rc = staged_d2h(h, xout, 1);
+            if (rc) return rc;
+        } else {
+            CK(cudaMemcpyAsync(points, d_pts, pts_bytes, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
     return finish_cloud(h);
 }
 
