@@ -173,7 +173,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
@@ -334,7 +334,7 @@ def run_gpu(args):
                 line["roofline"]["traffic"] = json.load(open(tpath))["dram_bytes_per_launch"]
             except Exception:
                 pass
-        print(json.dumps(line))
+        emit_line(line)
     for h in handles:
         h.close()
     if world > 1:
@@ -343,6 +343,27 @@ def run_gpu(args):
 
 
 T_START = time.perf_counter()
+
+# stdout carries exactly ONE line, the JSON result: everything libraries print while the benchmark runs (NCCL's
+# version banner, torchrun notices) is sent to stderr instead.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -354,4 +375,5 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.impl == "ours" and a.warmup < 3:
         a.warmup = 3  # timing rule: at least 3 warm-up steps
+    claim_stdout()
     sys.exit(run_reference(a) if a.impl == "reference" else run_gpu(a))
