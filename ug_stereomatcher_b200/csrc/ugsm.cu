@@ -916,9 +916,37 @@ std::vector<HostChunk> make_chunks(const HostXfer* x, int n, char* pinned) {
     return ch;
 }
 
+// Start up to `want` copy threads; never throws (no exception may cross the C-ABI).  Returns how many run.
+template <class F>
+int start_threads(std::vector<std::thread>& pool, int want, F&& work) {
+    try {
+        pool.reserve(want);
+        for (int t = 0; t < want; t++) pool.emplace_back(work);
+    } catch (...) {
+    }
+    return (int)pool.size();
+}
+
 // caller (pageable) -> pinned -> device.  Copy threads fill chunks in any order; the calling thread enqueues
 // the DMA of a chunk as soon as it is filled, in order.
+int staged_h2d_impl(ugsm_handle* h, const HostXfer* x, int n);
+int staged_d2h_impl(ugsm_handle* h, const HostXfer* x, int n);
 int staged_h2d(ugsm_handle* h, const HostXfer* x, int n) {
+    try {
+        return staged_h2d_impl(h, x, n);
+    } catch (...) {
+        return fail(h, UGSM_ERR_NOMEM, "staged H2D: host allocation failed");
+    }
+}
+int staged_d2h(ugsm_handle* h, const HostXfer* x, int n) {
+    try {
+        return staged_d2h_impl(h, x, n);
+    } catch (...) {
+        return fail(h, UGSM_ERR_NOMEM, "staged D2H: host allocation failed");
+    }
+}
+
+int staged_h2d_impl(ugsm_handle* h, const HostXfer* x, int n) {
     const std::vector<HostChunk> ch = make_chunks(x, n, h->pin_in);
     const int total = (int)ch.size();
     std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[total]);
@@ -933,7 +961,7 @@ int staged_h2d(ugsm_handle* h, const HostXfer* x, int n) {
         }
     };
     std::vector<std::thread> pool;
-    for (int t = 0; t < h->host_threads; t++) pool.emplace_back(work);
+    if (start_threads(pool, h->host_threads, work) == 0) work();  // no thread could be started: copy inline
     cudaError_t err = cudaSuccess;
     for (int c = 0; c < total; c++) {
         while (!done[c].load(std::memory_order_acquire)) std::this_thread::yield();
@@ -946,7 +974,7 @@ int staged_h2d(ugsm_handle* h, const HostXfer* x, int n) {
 
 // device -> pinned -> caller (pageable).  Called right after the producing kernels were enqueued: the copy
 // threads first pre-fault the caller's pages (while the GPU is busy), then follow the D2H DMA chunk by chunk.
-int staged_d2h(ugsm_handle* h, const HostXfer* x, int n) {
+int staged_d2h_impl(ugsm_handle* h, const HostXfer* x, int n) {
     const std::vector<HostChunk> ch = make_chunks(x, n, h->pin_out);
     const int total = (int)ch.size();
     while ((int)h->chunk_ev.size() < total) {
@@ -960,10 +988,11 @@ int staged_d2h(ugsm_handle* h, const HostXfer* x, int n) {
     }
     std::atomic<int> next_touch(0), next(0), touch_done(0);
     std::atomic<int> failed(0);
-    const int nthreads = h->host_threads;
+    std::atomic<int> nthreads(0);  // published once every thread that will run has been started
     const int device = h->device;
     auto work = [&]() {
         cudaSetDevice(device);
+        while (nthreads.load(std::memory_order_acquire) == 0) std::this_thread::yield();
         for (;;) {  // first touch of the output pages, one write per 4 KB page
             const int c = next_touch.fetch_add(1);
             if (c >= total) break;
@@ -972,7 +1001,8 @@ int staged_d2h(ugsm_handle* h, const HostXfer* x, int n) {
         }
         // no thread may write results before every thread has stopped writing zeros
         touch_done.fetch_add(1, std::memory_order_acq_rel);
-        while (touch_done.load(std::memory_order_acquire) < nthreads) std::this_thread::yield();
+        while (touch_done.load(std::memory_order_acquire) < nthreads.load(std::memory_order_acquire))
+            std::this_thread::yield();
         for (;;) {
             const int c = next.fetch_add(1);
             if (c >= total) break;
@@ -984,7 +1014,9 @@ int staged_d2h(ugsm_handle* h, const HostXfer* x, int n) {
         }
     };
     std::vector<std::thread> pool;
-    for (int t = 0; t < nthreads; t++) pool.emplace_back(work);
+    const int started = start_threads(pool, h->host_threads, work);
+    nthreads.store(started > 0 ? started : 1, std::memory_order_release);
+    if (started == 0) work();  // no thread could be started: copy inline
     for (auto& t : pool) t.join();
     if (failed.load()) return fail(h, UGSM_ERR_CUDA, "staged D2H failed: %s", cudaGetErrorString(cudaGetLastError()));
     return UGSM_OK;
