@@ -46,9 +46,9 @@ int main(int argc, char** argv) {
     rd(f, P1, sizeof P1);
     rd(f, P2, sizeof P2);
     cv::Mat dX(rows, cols, CV_32F), dY(rows, cols, CV_32F), img(im_rows, im_cols, CV_8UC3);
-    rd(f, dX.data(), (size_t)rows * cols * 4);
-    rd(f, dY.data(), (size_t)rows * cols * 4);
-    rd(f, img.data(), (size_t)im_rows * im_cols * 3);
+    rd(f, dX.data, (size_t)rows * cols * 4);
+    rd(f, dY.data, (size_t)rows * cols * 4);
+    rd(f, img.data, (size_t)im_rows * im_cols * 3);
     fclose(f);
 
     // stdout carries the node's progress bar; silence it

@@ -1,8 +1,11 @@
 // pc_stubs.h -- TEST INFRASTRUCTURE.  Minimal stand-ins for the ROS / OpenCV / PCL / cv_bridge
-// declarations that the reference's point-cloud node (src/pointcloud/getPointCloud.cpp) names, so
-// that the UNMODIFIED reference source compiles on a box with none of those libraries and its
-// triangulation code (PC:697-884 cloud loops, PC:886-1019 closed-form point, PC:375-484 fovea
-// coordinate mapping) can be executed by oracle/refbuild/refpc_main.cpp to pin the oracle.
+// declarations that the reference's two node sources name, so that the UNMODIFIED reference sources
+// compile on a box with none of those libraries:
+//   * src/pointcloud/getPointCloud.cpp: its triangulation code (PC:697-884 cloud loops, PC:886-1019
+//     closed-form point, PC:375-484 fovea coordinate mapping) is executed by refpc_main.cpp to pin the oracle;
+//   * src/gpu_matcher/UG_GPU_matcher.cpp: the matcher node, compiled against include/MatchGPULib.h and run
+//     by refnode_main.cpp to show that it consumes this repo's library unchanged.
+// Messages a node publishes are captured in ugsm_stub::published (topic -> last image).
 //
 // Only data containers and no-op plumbing live here: every arithmetic statement that is executed
 // comes from the reference file itself.  Nothing here is copied from ROS, OpenCV or PCL; the types
@@ -19,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <map>
 #include <memory>
 #include <sstream>
 #include <string>
@@ -75,7 +79,9 @@ inline size_t stub_elem_size(int type) {
 class Mat {
 public:
     int rows, cols;
-    Mat() : rows(0), cols(0), type_(0) {}
+    unsigned char* data;  // first byte (shared between copies, like cv::Mat)
+    size_t step;          // bytes per row
+    Mat() : rows(0), cols(0), data(nullptr), step(0), type_(0) {}
     Mat(int r, int c, int type) { create(r, c, type); }
     Mat(Size s, int type) { create(s.height, s.width, type); }
     void create(int r, int c, int type) {
@@ -83,22 +89,27 @@ public:
         cols = c;
         type_ = type;
         buf_ = std::make_shared<std::vector<unsigned char> >((size_t)r * c * stub_elem_size(type), 0);
+        data = buf_->data();
+        step = (size_t)c * stub_elem_size(type);
     }
     static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
     Mat clone() const {
         Mat m;
-        m.rows = rows, m.cols = cols, m.type_ = type_;
-        if (buf_) m.buf_ = std::make_shared<std::vector<unsigned char> >(*buf_);
+        m.rows = rows, m.cols = cols, m.type_ = type_, m.step = step;
+        if (buf_) {
+            m.buf_ = std::make_shared<std::vector<unsigned char> >(*buf_);
+            m.data = m.buf_->data();
+        }
         return m;
     }
     void release() {
         buf_.reset();
+        data = nullptr;
         rows = cols = 0;
     }
     bool empty() const { return !buf_ || rows == 0 || cols == 0; }
     int type() const { return type_; }
     Size size() const { return Size(cols, rows); }
-    unsigned char* data() { return buf_->data(); }
     template <class T>
     T* ptr(int r) {
         return reinterpret_cast<T*>(buf_->data() + (size_t)r * cols * stub_elem_size(type_));
@@ -131,6 +142,7 @@ inline void resize(const Mat&, Mat&, Size, double, double, int) {
     fprintf(stderr, "pc_stubs: cv::resize is not available (resized clouds are out of scope)\n");
     abort();
 }
+inline bool imwrite(const std::string&, const Mat&, const std::vector<int>& = std::vector<int>()) { return false; }
 inline int64 getTickCount() { return 0; }
 inline double getTickFrequency() { return 1.0; }
 }  // namespace cv
@@ -145,10 +157,12 @@ namespace sensor_msgs {
 struct Image {
     std_msgs::Header header;
     unsigned height, width;
+    std::string encoding;
     cv::Mat payload;  // the stub carries the pixels directly
     Image() : height(0), width(0) {}
 };
 typedef std::shared_ptr<const Image> ImageConstPtr;
+typedef std::shared_ptr<Image> ImagePtr;
 struct CameraInfo {
     unsigned height, width;
     std::vector<double> D;
@@ -172,6 +186,7 @@ struct DisparityImage {
     sensor_msgs::Image image;
 };
 typedef std::shared_ptr<const DisparityImage> DisparityImageConstPtr;
+typedef std::shared_ptr<DisparityImage> DisparityImagePtr;
 }  // namespace stereo_msgs
 namespace ug_stereomatcher {
 struct foveatedstack {
@@ -180,17 +195,50 @@ struct foveatedstack {
     sensor_msgs::Image image_stack;
 };
 typedef std::shared_ptr<const foveatedstack> foveatedstackConstPtr;
+struct GetDisparitiesGPU {  // srv/GetDisparitiesGPU.srv
+    struct Request {
+        sensor_msgs::Image imL, imR;
+    };
+    struct Response {
+        stereo_msgs::DisparityImage dispH, dispV, dispC;
+        foveatedstack fdispH, fdispV, fdispC;
+    };
+};
 }  // namespace ug_stereomatcher
+
+namespace ugsm_stub {
+inline std::map<std::string, cv::Mat>& published() {
+    static std::map<std::string, cv::Mat> m;
+    return m;
+}
+inline std::map<std::string, int>& params() {
+    static std::map<std::string, int> m;
+    return m;
+}
+}  // namespace ugsm_stub
 
 // ---------------------------------------------------------------- cv_bridge
 namespace cv_bridge {
 struct CvImage {
+    std_msgs::Header header;
+    std::string encoding;
     cv::Mat image;
+    sensor_msgs::ImagePtr toImageMsg() const {
+        sensor_msgs::ImagePtr m(new sensor_msgs::Image);
+        m->header = header;
+        m->encoding = encoding;
+        m->height = image.rows;
+        m->width = image.cols;
+        m->payload = image.clone();
+        return m;
+    }
 };
 typedef std::shared_ptr<CvImage> CvImagePtr;
 struct Exception : std::exception {};
-inline CvImagePtr toCvCopy(const sensor_msgs::Image& m, const std::string&) {
+inline CvImagePtr toCvCopy(const sensor_msgs::Image& m, const std::string& encoding) {
     CvImagePtr p(new CvImage);
+    p->header = m.header;
+    p->encoding = encoding;
     p->image = m.payload.clone();
     return p;
 }
@@ -200,21 +248,42 @@ inline CvImagePtr toCvCopy(const sensor_msgs::ImageConstPtr& m, const std::strin
 // ---------------------------------------------------------------- ROS plumbing (inert)
 namespace ros {
 struct Publisher {
+    std::string topic;
     int getNumSubscribers() const { return 0; }
+    void publish(const stereo_msgs::DisparityImagePtr& m) const { ugsm_stub::published()[topic] = m->image.payload; }
+    void publish(const ug_stereomatcher::foveatedstack& m) const {
+        ugsm_stub::published()[topic] = m.image_stack.payload;
+    }
     template <class T>
     void publish(const T&) const {}
 };
+struct ServiceServer {};
 struct NodeHandle {
-    bool hasParam(const std::string&) const { return false; }
-    template <class T>
-    bool getParam(const std::string&, T&) const {
-        return false;
+    bool hasParam(const std::string& name) const { return ugsm_stub::params().count(name) != 0; }
+    bool getParam(const std::string& name, int& v) const {
+        if (!hasParam(name)) return false;
+        v = ugsm_stub::params()[name];
+        return true;
     }
     template <class T>
-    Publisher advertise(const std::string&, int) {
-        return Publisher();
+    Publisher advertise(const std::string& topic, int) {
+        Publisher p;
+        p.topic = topic;
+        return p;
+    }
+    template <class M, class O>
+    ServiceServer advertiseService(const std::string&, M, O*) {
+        return ServiceServer();
     }
 };
+struct WallDuration {
+    double toSec() const { return 0.0; }
+};
+struct WallTime {
+    static WallTime now() { return WallTime(); }
+    WallDuration operator-(const WallTime&) const { return WallDuration(); }
+};
+inline bool ok() { return false; }
 inline void init(int&, char**, const std::string&) {}
 struct MultiThreadedSpinner {
     explicit MultiThreadedSpinner(int) {}

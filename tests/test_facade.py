@@ -90,3 +90,22 @@ def test_python_mirror(capi, oracle):
     want = oracle.match_composite(L, R)
     assert (Hc == want[0]).all() and (Vc == want[1]).all() and (Cc == want[2]).all()
     m.close()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/gpu_matcher/UG_GPU_matcher.cpp"),
+                    reason="needs the reference checkout")
+def test_reference_node_source_builds_against_the_facade(capi, tmp_path):
+    """The reference's matcher node (UG_GPU_matcher.cpp), unmodified, compiles against include/MatchGPULib.h and
+    links with libugsm.so (ROS / OpenCV / cv_bridge replaced by inert stand-ins).  CPU-only: compile + link."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "refnode")
+    cmd = ["/usr/bin/g++", "-O0", "-std=c++14", "-fpermissive", "-w", "-DUGSM_WITH_CV_BRIDGE",
+           "-I" + os.path.join(root, "oracle", "refbuild", "stubs_pc"), "-I" + os.path.join(root, "include"),
+           "-I/root/reference/include", "-I/root/reference", "-o", exe,
+           os.path.join(root, "oracle", "refbuild", "refnode_main.cpp"),
+           os.path.join(root, "ug_stereomatcher_b200", "csrc", "MatchGPULib.cpp"),
+           "-L" + os.path.join(root, "ug_stereomatcher_b200"), "-lugsm",
+           "-Wl,-rpath," + os.path.join(root, "ug_stereomatcher_b200")]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr.decode()[-3000:]
+    assert os.path.exists(exe)
