@@ -118,3 +118,22 @@ def test_point_order_stride_and_colour(oracle):
     # an RGB-ordered image gives the same colours with bgr=False
     p_rgb = oracle.cloud_full(P1, P2, dX, dY, img[:, :, ::-1], bgr=False, sampling=s)
     assert np.array_equal(p_rgb.view(np.uint32), p4.view(np.uint32))
+
+
+@pytest.mark.skipif(not os.path.exists(REFPC), reason="oracle/_ref/refpc not built (needs /root/reference)")
+def test_reference_binary_timing(oracle, tmp_path):
+    """The reference's own per-pixel host loop (single thread, like the node) on a 1 MP plane, scaled to 16 MP:
+    the CPU figure quoted beside the K5 kernel time in profiles/README.md (run with -s to see it)."""
+    import time
+
+    rows, cols = 816, 1232
+    rng = np.random.default_rng(3)
+    P1, P2 = cameras(rng, cols, rows)
+    dX = rng.normal(0, 8, (rows, cols)).astype(np.float32)
+    dY = rng.normal(0, 1, (rows, cols)).astype(np.float32)
+    img = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    t0 = time.perf_counter()
+    ref = oracle.run_refpc(0, P1, P2, dX, dY, img, workdir=str(tmp_path))
+    dt = time.perf_counter() - t0
+    assert ref.shape == (rows * cols, 4)
+    print("reference point-cloud loop: %.2f s per 1 MP incl. file I/O -> %.1f s per 16 MP cloud" % (dt, dt * 16))

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Point-cloud step (K5) at BASELINE sizes on one B200: kernel time from CUDA events inside the library,
-roofline fraction against MEASURED_PEAKS.json, the pair + cloud path with the planes staying on the
-device, and the CPU implementations beside it (the oracle port on all cores; the unmodified reference
-source oracle/_ref/refpc, single-threaded like the node, on a 4 MP sample).  Prints JSON lines."""
+roofline fraction against MEASURED_PEAKS.json, and the pair + cloud path with the planes staying on the
+device.  Prints JSON lines.  (The CPU implementations are timed beside it by the tests, which are allowed to
+run the oracle: tests/test_gpu_cloud.py::test_16mp_full_cloud_vs_oracle and
+tests/test_cloud_oracle.py::test_reference_binary_timing, both with `pytest -s`.)"""
 import json
 import os
 import sys
@@ -10,7 +11,6 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import numpy as np
 import torch
@@ -74,24 +74,6 @@ def main():
             t.append((time.perf_counter() - t0) * 1e3)
         print(json.dumps({"what": "16MP pair (device-resident images) + cloud to pinned host memory (257 MB D2H)",
                           "pair_device_ms": pair_ms, "wall_ms": float(np.median(t[1:]))}), flush=True)
-        H, V = outs[0].cpu().numpy(), outs[1].cpu().numpy()
-    # CPU beside it
-    import ugsm_oracle as o
-
-    t0 = time.perf_counter()
-    want = o.cloud_full(P1, P2, H, V, L, bgr=False)
-    cpu_s = time.perf_counter() - t0
-    print(json.dumps({"what": "oracle port on the host cores, 16MP cloud", "seconds": cpu_s,
-                      "threads": o.num_threads(), "bit_exact_vs_gpu": bool(np.array_equal(
-                          want.view(np.uint32), pts.view(np.uint32)))}), flush=True)
-    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "refpc")):
-        sub = (slice(0, 1632), slice(0, 2464))
-        t0 = time.perf_counter()
-        ref = o.run_refpc(0, P1, P2, H[sub], V[sub], np.ascontiguousarray(L[sub][:, :, ::-1]), workdir="/tmp")
-        ref_s = time.perf_counter() - t0
-        print(json.dumps({"what": "unmodified reference source (oracle/_ref/refpc, 1 thread, incl. file I/O) on a "
-                                  "2464x1632 crop", "seconds": ref_s, "scaled_to_16MP_seconds": ref_s * 4.0,
-                          "points": int(ref.shape[0])}), flush=True)
 
 
 if __name__ == "__main__":
