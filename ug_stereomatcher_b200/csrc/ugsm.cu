@@ -86,6 +86,8 @@ struct ugsm_handle {
     int launches = 0;
     bool k_attr_set = false;
     int k1_nw = 2;
+    long k1_small_pixels = 400000;  // levels below this use k1_correlate_small (UGSM_K1_SMALL_PIXELS)
+    long k2_small_pixels = 700000;  // levels below this use k2_smooth_box_small (UGSM_K2_SMALL_PIXELS)
     int k0_rows_dense = 16, k0_rows_dec = 8;  // output rows per warp of k0_march5 (UGSM_K0_ROWS_DENSE / _DEC)
     // CUDA graph of the per-pair launch sequence (pyramid levels .. last level), valid for the current shape
     cudaGraphExec_t graph_exec = nullptr;
@@ -214,8 +216,6 @@ int compute_dims(const ugsm_config& c, int rows, int cols, int mode, ugsm_dims* 
 // ------------------------------------------------------------------ kernel launchers
 constexpr int K1_TH = 16;
 constexpr int K1S_TH = 8;
-constexpr long K1_SMALL_PIXELS = 400000;  // levels below this use k1_correlate_small
-constexpr long K2_SMALL_PIXELS = 700000;  // levels below this use k2_smooth_box_small
 // K0: the register-marching kernels win on large planes (HBM-bound), the tiled one on small planes (latency-bound)
 constexpr long K0_MARCH_DENSE_PIXELS = 900000;  // output pixels
 constexpr long K0_MARCH_DEC_PIXELS = 200000;
@@ -232,6 +232,8 @@ int set_kernel_attrs(ugsm_handle* h) {
     CK(cudaFuncSetAttribute(k1_correlate<2, K1_TH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     if (const char* e = getenv("UGSM_K1_NW")) h->k1_nw = atoi(e);  // tuning override: warps per K1 CTA (2 or 4)
+    if (const char* e = getenv("UGSM_K1_SMALL_PIXELS")) h->k1_small_pixels = atol(e);
+    if (const char* e = getenv("UGSM_K2_SMALL_PIXELS")) h->k2_small_pixels = atol(e);
     if (const char* e = getenv("UGSM_K0_ROWS_DENSE")) h->k0_rows_dense = atoi(e) > 0 ? atoi(e) : h->k0_rows_dense;
     if (const char* e = getenv("UGSM_K0_ROWS_DEC")) h->k0_rows_dec = atoi(e) > 0 ? atoi(e) : h->k0_rows_dec;
     CK(cudaFuncSetAttribute(k2_smooth_box, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -245,7 +247,7 @@ void launch_k1(ugsm_handle* h, const K1Params& p) {
     // 30 x 8 tiles with one warp per colour channel, so that the few tiles there spread over
     // more SMs and the dependent chain per launch is short.
     const int band_rows = p.y_end - p.y_begin;
-    const bool big = (long)p.w * p.h >= K1_SMALL_PIXELS || band_rows != p.h;  // a row band always uses the band-aware kernel
+    const bool big = (long)p.w * p.h >= h->k1_small_pixels || band_rows != p.h;  // a row band always uses the band-aware kernel
     if (big && h->k1_nw == 2) {
         dim3 grid(div_up(p.w, 60), div_up(band_rows, K1_TH));
         k1_correlate<2, K1_TH><<<grid, 64, sizeof(K1Smem<2, K1_TH>), h->stream>>>(p);
@@ -278,7 +280,7 @@ void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci
     p.passes = passes;
     p.a1 = h->taps.a[1];
     const int R = passes + 1;
-    if (!banded && (long)w * hh < K2_SMALL_PIXELS && K2S_T + 2 * R <= 32) {
+    if (!banded && (long)w * hh < h->k2_small_pixels && K2S_T + 2 * R <= 32) {
         // small levels: 16x16 tiles, one thread per region cell (latency-oriented)
         p.th = K2S_T;
         p.hpad = R;
