@@ -331,7 +331,19 @@ def run_gpu(args):
         tpath = os.path.join(ROOT, "profiles", "traffic_k1.json")
         if os.path.exists(tpath):
             try:
-                line["roofline"]["traffic"] = json.load(open(tpath))["dram_bytes_per_launch"]
+                prof = json.load(open(tpath))
+                line["roofline"]["traffic"] = prof["dram_bytes_per_launch"]
+                # K1 is bounded by instruction issue, not by HBM: say how close it runs to THAT bound as well
+                # (executed warp-instructions of the ncu capture / live launch time, against 4 issue slots per
+                # SM per clock at the SM clock sampled under load)
+                wi, mhz = prof.get("warp_instructions_per_launch"), clocks.get("sm_mhz")
+                if wi and mhz and k1_avg:
+                    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                    peak_issue = sms * 4 * mhz * 1e6  # warp-instructions / s
+                    line["roofline"]["issue_bound"] = {
+                        "warp_instructions_per_launch": wi, "achieved_ginst_per_s": wi / (k1_avg * 1e-3) / 1e9,
+                        "peak_ginst_per_s": peak_issue / 1e9, "frac": wi / (k1_avg * 1e-3) / peak_issue,
+                        "note": "secondary bound: the kernel executes 1185 instructions per pixel-iteration"}
             except Exception:
                 pass
         emit_line(line)
