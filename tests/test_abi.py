@@ -91,3 +91,24 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "ugsm_oracle" not in text and "ugsmo_" not in text, os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C-ABI: include/ugsm.h must compile as C99 (no C++ or CUDA types in the signatures),
+    and a C program must link against the library and reach the host-only entry points."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use.c"
+    src.write_text('#include <stdio.h>\n#include "ugsm.h"\n'
+                   'int main(void) { ugsm_config c; ugsm_dims d; ugsm_config_default(&c);\n'
+                   '  if (ugsm_query_dims(&c, 3264, 4928, 1, &d) != UGSM_OK) return 2;\n'
+                   '  printf("%d %d %d %s\\n", c.levels, d.fov_width, d.fov_height, ugsm_version()); return 0; }\n')
+    exe = str(tmp_path / "use")
+    lib_dir = os.path.join(root, "ug_stereomatcher_b200")
+    p = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                        "-o", exe, str(src), "-L" + lib_dir, "-lugsm", "-Wl,-rpath," + lib_dir],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr.decode()
+    out = subprocess.run([exe], stdout=subprocess.PIPE).stdout.decode().split()
+    assert out[:3] == ["14", "615", "407"]
