@@ -97,6 +97,12 @@ int ugsm_destroy(ugsm_handle* h);
 /* Last error text of this handle (never NULL).  With h == NULL: last creation error. */
 const char* ugsm_last_error(const ugsm_handle* h);
 
+/* Page-locked host memory (portable across devices) for hosts that have no CUDA toolchain of their own: buffers
+ * from here make the copies of ugsm_match_* plain asynchronous DMA.  Any other host memory works too (pageable
+ * buffers are staged through pinned chunks by copy threads).  Failure text: ugsm_last_error(NULL). */
+int ugsm_host_alloc(size_t bytes, void** out);
+int ugsm_host_free(void* p);
+
 /* Use an external CUDA stream (cudaStream_t passed as void*); NULL restores the handle's own. */
 int ugsm_set_stream(ugsm_handle* h, void* cuda_stream);
 

@@ -109,3 +109,35 @@ def test_reference_node_source_builds_against_the_facade(capi, tmp_path):
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert p.returncode == 0, p.stderr.decode()[-3000:]
     assert os.path.exists(exe)
+
+
+BATCH = os.path.join(ROOT, "ug_stereomatcher_b200", "ugsm_batch")
+
+
+def test_batch_driver_fails_loudly_without_gpu(capi):
+    if _have_gpu():
+        pytest.skip("GPU present")
+    assert os.path.exists(BATCH)
+    p = subprocess.run([BATCH, "240", "320", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 3 and b"no CPU fallback" in p.stderr and p.stdout == b""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("foveated", [False, True])
+def test_batch_driver_streams_pairs_and_matches_cabi(capi, tmp_path, foveated):
+    """ugsm_batch: worker threads with one handle + pinned buffers each (ugsm_host_alloc) pull pairs from a shared
+    counter; every pair of the batch is the same image pair here, so the last result must equal the single call."""
+    import json
+
+    L, R, _, _ = synth.make_pair(640, 480, 3)
+    L.tofile(tmp_path / "l.rgb")
+    R.tofile(tmp_path / "r.rgb")
+    cmd = [BATCH, "480", "640", "7", "--in-flight", "3", "--left", str(tmp_path / "l.rgb"), "--right",
+           str(tmp_path / "r.rgb")] + (["--foveated"] if foveated else [])
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr.decode()
+    rec = json.loads(p.stdout.decode())
+    assert rec["pairs"] == 7 and rec["gpus"] == 1 and rec["in_flight_per_gpu"] == 3 and rec["pairs_per_s"] > 0
+    with capi.Handle() as h:
+        want = h.match_foveated(L, R)[0] if foveated else h.match_full(L, R)[0]
+    assert rec["h_sum"] == pytest.approx(float(want.astype(np.float64).sum()), rel=1e-9, abs=1e-6)

@@ -26,7 +26,7 @@ SYMBOLS = [
     "ugsm_stage_match_level", "ugsm_bench_correlate", "ugsm_bench_smooth", "ugsm_bench_null", "ugsm_version", "ugsm_band_begin",
     "ugsm_band_level_info", "ugsm_band_iteration", "ugsm_band_upsample", "ugsm_band_emit", "ugsm_band_pack",
     "ugsm_band_unpack", "ugsm_cloud_count", "ugsm_cloud_full", "ugsm_cloud_full_device", "ugsm_cloud_foveated",
-    "ugsm_cloud_from_match", "ugsm_cloud_last_ms", "ugsm_bench_pyramid",
+    "ugsm_cloud_from_match", "ugsm_cloud_last_ms", "ugsm_bench_pyramid", "ugsm_host_alloc", "ugsm_host_free",
 ]
 
 
@@ -147,6 +147,8 @@ def lib():
         L.ugsm_bench_smooth.argtypes = [vp, i, i, i, i, C.POINTER(C.c_float)]
         L.ugsm_bench_null.argtypes = [vp, i, C.POINTER(C.c_float)]
         L.ugsm_bench_pyramid.argtypes = [vp, i, i, i, i, C.POINTER(C.c_float)]
+        L.ugsm_host_alloc.argtypes = [sz, C.POINTER(vp)]
+        L.ugsm_host_free.argtypes = [vp]
         L.ugsm_band_begin.argtypes = [vp, vp, vp, i, i, sz, i]
         L.ugsm_band_level_info.argtypes = [vp, i, C.POINTER(BandLevel)]
         L.ugsm_band_iteration.argtypes = [vp, i, i, i, i, i]

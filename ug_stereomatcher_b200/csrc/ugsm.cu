@@ -1298,6 +1298,25 @@ int ugsm_stage_composite(ugsm_handle* h, const float* stackH, const float* stack
     return UGSM_OK;
 }
 
+// ---- pinned host memory for hosts without a CUDA toolchain of their own ----
+int ugsm_host_alloc(size_t bytes, void** out) {
+    if (!out || bytes == 0) return UGSM_ERR_INVALID;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = std::string("ugsm_host_alloc: ") + cudaGetErrorString(e);
+        *out = nullptr;
+        return e == cudaErrorMemoryAllocation ? UGSM_ERR_NOMEM : UGSM_ERR_NO_DEVICE;
+    }
+    return UGSM_OK;
+}
+
+int ugsm_host_free(void* p) {
+    if (!p) return UGSM_OK;
+    return cudaFreeHost(p) == cudaSuccess ? UGSM_OK : UGSM_ERR_CUDA;
+}
+
 // ---- point cloud entry points (K5) ----
 int ugsm_cloud_count(int rows, int cols, int sampling, int64_t* npoints) {
     if (rows < 1 || cols < 1 || sampling < 1 || !npoints) return UGSM_ERR_INVALID;
