@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "ugsm_kernels.cuh"
+#include "ugsm_k1_stream.cuh"
 
 using namespace ugsm;
 
@@ -86,6 +87,11 @@ struct ugsm_handle {
     int launches = 0;
     bool k_attr_set = false;
     int k1_nw = 2;
+    int k1_stream = 1;        // large levels use the streaming strip march k1_stream (UGSM_K1_STREAM=0: the tiled k1_correlate)
+    int k1s_slots = 0;        // co-resident k1_stream CTAs on the device (occupancy x SM count)
+    int k1s_min_seg = 32;     // shortest row segment of a strip (UGSM_K1S_MIN_SEG)
+    int* d_flags = nullptr;   // per level: nonzero when the six matcher planes lie in [1, 256] (k1_stream FAST march)
+    int k1_fast = 1;          // UGSM_K1_FAST=0: always take the guarded GENERIC march
     long k1_small_pixels = 400000;  // levels below this use k1_correlate_small (UGSM_K1_SMALL_PIXELS)
     long k2_small_pixels = 700000;  // levels below this use k2_smooth_box_small (UGSM_K2_SMALL_PIXELS)
     int k0_rows_dense = 16, k0_rows_dec = 8;  // output rows per warp of k0_march5 (UGSM_K0_ROWS_DENSE / _DEC)
@@ -232,6 +238,16 @@ int set_kernel_attrs(ugsm_handle* h) {
     CK(cudaFuncSetAttribute(k1_correlate<2, K1_TH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
     if (const char* e = getenv("UGSM_K1_NW")) h->k1_nw = atoi(e);  // tuning override: warps per K1 CTA (2 or 4)
+    if (const char* e = getenv("UGSM_K1_STREAM")) h->k1_stream = atoi(e);
+    if (const char* e = getenv("UGSM_K1_FAST")) h->k1_fast = atoi(e);
+    if (const char* e = getenv("UGSM_K1S_MIN_SEG")) h->k1s_min_seg = atoi(e) > 0 ? atoi(e) : h->k1s_min_seg;
+    {
+        CK(cudaFuncSetAttribute(k1_stream, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1_stream, K1S_NW * 32, K1S_NW * sizeof(K1Ring)));
+        h->k1s_slots = std::max(1, nb) * h->sm_count;
+        if (const char* e = getenv("UGSM_K1S_SLOTS")) h->k1s_slots = atoi(e) > 0 ? atoi(e) : h->k1s_slots;
+    }
     if (const char* e = getenv("UGSM_K1_SMALL_PIXELS")) h->k1_small_pixels = atol(e);
     if (const char* e = getenv("UGSM_K2_SMALL_PIXELS")) h->k2_small_pixels = atol(e);
     if (const char* e = getenv("UGSM_K0_ROWS_DENSE")) h->k0_rows_dense = atoi(e) > 0 ? atoi(e) : h->k0_rows_dense;
@@ -242,13 +258,24 @@ int set_kernel_attrs(ugsm_handle* h) {
     return UGSM_OK;
 }
 
-void launch_k1(ugsm_handle* h, const K1Params& p) {
-    // Large levels: 4-warp CTAs (120 columns x 16 rows), channels in sequence.  Small levels:
-    // 30 x 8 tiles with one warp per colour channel, so that the few tiles there spread over
-    // more SMs and the dependent chain per launch is short.
+void launch_k1(ugsm_handle* h, const K1Params& p, const int* fast_flag = nullptr) {
+    // Large levels: streaming strip march (k1_stream): one warp per 30-column strip and row segment; the
+    // segment length is chosen so that all CTAs of the launch are co-resident (one wave, no tail).
+    // Small levels: 30 x 8 tiles with one warp per colour channel, so that the few tiles there spread
+    // over more SMs and the dependent chain per launch is short.
     const int band_rows = p.y_end - p.y_begin;
-    const bool big = (long)p.w * p.h >= h->k1_small_pixels || band_rows != p.h;  // a row band always uses the band-aware kernel
-    if (big && h->k1_nw == 2) {
+    const bool big = (long)p.w * p.h >= h->k1_small_pixels || band_rows != p.h;  // a row band always uses a band-aware kernel
+    if (big && h->k1_stream) {
+        K1StreamParams sp;
+        sp.k = p;
+        sp.fast_flag = h->k1_fast ? fast_flag : nullptr;
+        const int strips = div_up(p.w, 30 * K1S_NW);
+        int nseg = std::max(1, h->k1s_slots / strips);
+        nseg = std::min(nseg, std::max(1, band_rows / h->k1s_min_seg));
+        sp.seg_rows = div_up(band_rows, nseg);
+        dim3 grid(strips, div_up(band_rows, sp.seg_rows));
+        k1_stream<<<grid, K1S_NW * 32, K1S_NW * sizeof(K1Ring), h->stream>>>(sp);
+    } else if (big && h->k1_nw == 2) {
         dim3 grid(div_up(p.w, 60), div_up(band_rows, K1_TH));
         k1_correlate<2, K1_TH><<<grid, 64, sizeof(K1Smem<2, K1_TH>), h->stream>>>(p);
     } else if (big) {
@@ -320,6 +347,21 @@ bool planes_aligned(const K0Planes& pl, int n, int spitch, int dpitch) {
     for (int k = 0; k < n; k++)
         if ((reinterpret_cast<uintptr_t>(pl.src[k]) & 15) || (reinterpret_cast<uintptr_t>(pl.dst[k]) & 15)) return false;
     return true;
+}
+
+// flag[0] = nonzero iff every value of the six matcher planes of a level lies in [1, 256]: the precondition of
+// k1_stream's FAST march (ugsm_k1_stream.cuh, k1s_fast_bounds).  Stays on the device: no host round trip.
+void launch_range_flag(ugsm_handle* h, const float* const* L, const float* const* R, int w, int hh, int pitch,
+                       int* flag) {
+    RangePlanes pl;
+    for (int k = 0; k < 3; k++) {
+        pl.p[k] = L[k];
+        pl.p[3 + k] = R[k];
+    }
+    cudaMemsetAsync(flag, 1, sizeof(int), h->stream);
+    dim3 grid(std::min(div_up(w, 1024), 8), std::min(hh, 512), 6);
+    k_range_flag<<<grid, 256, 0, h->stream>>>(pl, w, hh, pitch, 1.0f, 256.0f, flag);
+    h->launches++;
 }
 
 // U = colT(rowT(L^2)) for `n` planes of equal dims in one launch.
@@ -504,13 +546,16 @@ void prepare_levels(ugsm_handle* h) {
             }
         }
         launch_energy(h, b.Lm, b.U, 3, b.mw, b.mh, b.mpitch);
+        const int i = (int)(&b - &h->lv[0]);
+        if (h->k1_stream && h->k1_fast && (long)b.mw * b.mh >= h->k1_small_pixels)
+            launch_range_flag(h, b.Lm, b.Rm, b.mw, b.mh, b.mpitch, h->d_flags + i);
     }
 }
 
 // MGL:1662-2489: `iters` iterations of K1 (correlate/fit/blend) + K2 (smooth/box).
 void run_level(ugsm_handle* h, float* const L[3], float* const R[3], float* const U[3], float* const st[3],
                float* const tmp[3], int w, int hh, int pitch, int iters, int passes, bool coarsest,
-               int timed_level = -1) {
+               int timed_level = -1, const int* fast_flag = nullptr) {
     float T = 1.0f;  // MGL:1673
     for (int m = 1; m <= iters; m++) {
         int slot = -1;
@@ -543,7 +588,7 @@ void run_level(ugsm_handle* h, float* const L[3], float* const R[3], float* cons
         p.dbg_bh = nullptr;
         p.dbg_bv = nullptr;
         p.tp = h->taps;
-        launch_k1(h, p);
+        launch_k1(h, p, fast_flag);
         if (slot >= 0) cudaEventRecord(h->kev[3 * slot + 1], h->stream);
         launch_k2(h, tmp[0], tmp[1], tmp[2], st[0], st[1], st[2], w, hh, pitch, passes);
         if (slot >= 0) cudaEventRecord(h->kev[3 * slot + 2], h->stream);
@@ -573,7 +618,7 @@ int run_levels(ugsm_handle* h, int hi, int lo, bool events) {
             }
         }
         run_level(h, b.Lm, b.Rm, b.U, b.st, h->tmp, b.mw, b.mh, b.mpitch, b.iters, b.smooth, i == levels - 1,
-                  (events && i < UGSM_TIMED_LEVELS) ? i : -1);
+                  (events && i < UGSM_TIMED_LEVELS) ? i : -1, h->d_flags + i);
         if (events) CK(cudaEventRecord(h->ev[4 + i], h->stream));
     }
     return UGSM_OK;
@@ -1099,6 +1144,11 @@ int ugsm_create(const ugsm_config* cfg, ugsm_handle** out) {
         return fail(nullptr, UGSM_ERR_CUDA, "stream creation: %s", cudaGetErrorString(e));
     }
     h->stream = h->own_stream;
+    if ((e = cudaMalloc(&h->d_flags, (UGSM_MAX_LEVELS + 1) * sizeof(int))) != cudaSuccess ||
+        (e = cudaMemset(h->d_flags, 0, (UGSM_MAX_LEVELS + 1) * sizeof(int))) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, UGSM_ERR_CUDA, "flag allocation: %s", cudaGetErrorString(e));
+    }
     for (auto& ev : h->ev) {
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) {
             delete h;
@@ -1131,6 +1181,7 @@ int ugsm_destroy(ugsm_handle* h) {
     for (auto& ev : h->cloud_ev)
         if (ev) cudaEventDestroy(ev);
     if (h->cloud_buf) cudaFree(h->cloud_buf);
+    if (h->d_flags) cudaFree(h->d_flags);
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
     for (auto& ev : h->chunk_ev)
@@ -1585,7 +1636,8 @@ int ugsm_stage_correlate(ugsm_handle* h, const float* L3, const float* R3, const
     p.dbg_bh = dbh;
     p.dbg_bv = dbv;
     p.tp = h->taps;
-    launch_k1(h, p);
+    launch_range_flag(h, d, d + 3, width, height, pitch, h->d_flags + UGSM_MAX_LEVELS);
+    launch_k1(h, p, h->d_flags + UGSM_MAX_LEVELS);
     CK(cudaGetLastError());
     CK(down2d(Hn, d[12], pitch, width, height, h->stream));
     CK(down2d(Vn, d[13], pitch, width, height, h->stream));
@@ -1668,7 +1720,9 @@ int ugsm_stage_match_level(ugsm_handle* h, const float* L3, const float* R3, flo
         CK(up2d(d[9 + k], pitch, io[k], width, height, h->stream));
     }
     launch_energy(h, d, d + 6, 3, width, height, pitch);
-    run_level(h, d, d + 3, d + 6, d + 9, d + 12, width, height, pitch, iters, passes, coarsest != 0);
+    launch_range_flag(h, d, d + 3, width, height, pitch, h->d_flags + UGSM_MAX_LEVELS);
+    run_level(h, d, d + 3, d + 6, d + 9, d + 12, width, height, pitch, iters, passes, coarsest != 0, -1,
+              h->d_flags + UGSM_MAX_LEVELS);
     CK(cudaGetLastError());
     for (int k = 0; k < 3; k++) CK(down2d(io[k], d[9 + k], pitch, width, height, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1779,7 +1833,7 @@ int ugsm_band_iteration(ugsm_handle* h, int level, int m, int y_begin, int y_end
     p.dbg_srcx = p.dbg_srcy = nullptr;
     p.dbg_bh = p.dbg_bv = nullptr;
     p.tp = h->taps;
-    launch_k1(h, p);
+    launch_k1(h, p, h->d_flags + level);
     launch_k2(h, h->tmp[0], h->tmp[1], h->tmp[2], b.st[0], b.st[1], b.st[2], b.mw, b.mh, b.mpitch, b.smooth, y_begin,
               y_end);
     CK(cudaGetLastError());
@@ -1890,12 +1944,14 @@ int ugsm_bench_correlate(ugsm_handle* h, int width, int height, int reps, float*
     p.dbg_srcx = p.dbg_srcy = nullptr;
     p.dbg_bh = p.dbg_bv = nullptr;
     p.tp = h->taps;
-    for (int i = 0; i < 3; i++) launch_k1(h, p);
+    launch_range_flag(h, d, d + 3, width, height, pitch, h->d_flags + UGSM_MAX_LEVELS);
+    const int* ff = h->d_flags + UGSM_MAX_LEVELS;
+    for (int i = 0; i < 3; i++) launch_k1(h, p, ff);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, h->stream));
-    for (int i = 0; i < reps; i++) launch_k1(h, p);
+    for (int i = 0; i < reps; i++) launch_k1(h, p, ff);
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaEventSynchronize(e1));
     float ms = 0;
