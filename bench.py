@@ -15,14 +15,19 @@ path ("scaling": "weak"); torch.distributed (NCCL) is only the barrier and the m
             one step = a batch of 4 pairs per GPU, in flight together on four handles/streams
             (pairs are independent units; this hides the latency-bound coarse levels of one
             pair -- and, end to end, the PCIe copies -- behind the others).
-            config.ms_per_pair_latency_device is the one-pair-in-flight latency.
+            run.ms_per_pair_latency_device is the one-pair-in-flight latency.
   e2e       pairs/s through the host-buffer C-ABI call (ugsm_match_full) with pinned host
-            buffers: H2D of both images and D2H of H,V,C inside the timed region, same batch in flight
+            buffers: H2D of both images and D2H of H, V, C inside the timed region, same batch in flight
   roofline  dominant kernel = K1 (fused warp+correlation+fit) at level 0, algorithmic bytes
             48 B/pixel (9 planes in, 3 out) / average launch time from CUDA
-            events recorded around every K1 launch of the timed steps, vs MEASURED_PEAKS.json
+            events recorded around every level-0 K1 launch of an instrumented handle (use_graph = 2;
+            the throughput regions replay the whole pair from a CUDA graph), vs MEASURED_PEAKS.json
+  foveated  BASELINE configs[3]: the same 16 MP pair in foveated mode (615x407 fovea per level):
+            ms/pair device-resident and end to end, and its dominant kernel's share of HBM peak
   cpu_baseline  the oracle (scalar C + OpenMP port of the reference kernels) timed on this
             box's host cores on a bounded sample, scaled by pixel-iterations
+
+`config` is the same object in both arms (the workload); everything specific to how an arm ran is under `run`.
 """
 import argparse
 import json
@@ -41,6 +46,23 @@ UNIT = "pairs/s"
 K1_BYTES_PER_PIXEL = 48  # L x3 + R x3 + (H,V,C) in, (H,V,C) out, f32
 PIXEL_ITERS_16MP = 131429636
 IN_FLIGHT = int(os.environ.get("UGSM_BENCH_IN_FLIGHT", "4"))  # pairs in flight per GPU in the throughput regions (independent handles/streams)
+SCALE = 1.41421356  # MatchLib_common.h:15
+
+
+def pixel_iterations(rows, cols, levels=14, cutoff=22):
+    """Sum over the levels of width * height * iterations (MatchGPULib.cpp:1224-1228, 1741), pure Python."""
+    w, h, total = cols, rows, 0
+    for i in range(levels):
+        total += w * h * (cutoff if i > 5 else 2 * (i + 1))
+        w, h = int(w / SCALE), int(h / SCALE)
+    return total
+
+
+def workload_config():
+    """The workload, identical in both arms."""
+    return {"workload": WORKLOAD, "shape": [ROWS, COLS], "levels": 14, "iterations": 218,
+            "pixel_iterations": PIXEL_ITERS_16MP, "outputs": "H, V, C float32 planes"}
+
 
 
 def _peaks():
@@ -109,58 +131,78 @@ class ClockSampler:
         return out
 
 
-def cpu_sample(target_seconds=20.0):
-    """Oracle on the host cores on a bounded sample of the workload; returns a cpu_baseline dict.
-    (The one place besides tests/ and smoke() where bench.py executes oracle/.)"""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import ugsm_oracle as oracle
-    from ug_stereomatcher_b200 import synth
+_SYNTH = None
 
-    cores = oracle.use_all_host_cores()
-    # calibrate on 640x480 (2.48 M pixel-iterations), then pick the largest sample that fits the budget
-    L, R, _, _ = synth.make_pair(640, 480, 0)
-    oracle.match_full(L[:64, :64].copy(), R[:64, :64].copy(), oracle.default_config(levels=3))  # spin up OpenMP
-    t0 = time.perf_counter()
-    oracle.match_full(L, R)
-    t_small = time.perf_counter() - t0
-    rate = 2480000.0 / t_small  # pixel-iterations / s (small images under-use the cores; conservative)
-    cands = [(4928, 3264, PIXEL_ITERS_16MP), (2464, 1632, 32790000), (1232, 816, 8180000)]
-    w, h, pi = cands[-1]
-    for cw, chh, cpi in cands:
-        if cpi / rate <= target_seconds * 1.6:
-            w, h, pi = cw, chh, cpi
-            break
-    L, R, _, _ = synth.make_pair(w, h, 0)
-    from ug_stereomatcher_b200 import capi
-    pi = int(capi.query_dims(capi.default_config(), h, w, 0).pixel_iterations)
-    t0 = time.perf_counter()
-    oracle.match_full(L, R)
-    t = time.perf_counter() - t0
-    t16 = t * PIXEL_ITERS_16MP / pi
-    return {
-        "value": 1.0 / t16, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": "oracle (scalar C + OpenMP port of the reference kernels) full-pyramid match of the same synthetic "
-                  "scene at %dx%d: %.2f s for %.2f M pixel-iterations, scaled by pixel-iterations to the 16 MP pair "
-                  "(131.43 M) -> %.1f s/pair" % (w, h, t, pi / 1e6, t16),
-        "seconds_sample": t, "seconds_per_pair_scaled": t16,
-    }
+
+def _synth():
+    """ug_stereomatcher_b200/synth.py loaded by path: the CPU legs must not import the package (whose capi binding
+    would be one call away from mapping libugsm.so into the reference arm)."""
+    global _SYNTH
+    if _SYNTH is None:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ugsm_synth", os.path.join(ROOT, "ug_stereomatcher_b200", "synth.py"))
+        _SYNTH = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_SYNTH)
+    return _SYNTH
+
+
+class CpuArm:
+    """The oracle on the host cores on a bounded sample of the workload (the one place besides tests/ and smoke()
+    where bench.py executes oracle/).  Calibrates once on 640x480, then every sample() is one full-pyramid match of
+    the same synthetic scene at the largest of 16 MP / 4 MP / 1 MP that fits `target_seconds`, scaled to the 16 MP
+    pair by pixel-iterations."""
+
+    def __init__(self, target_seconds):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ugsm_oracle as oracle
+
+        self.oracle = oracle
+        self.cores = oracle.use_all_host_cores()
+        synth = _synth()
+        L, R, _, _ = synth.make_pair(640, 480, 0)
+        oracle.match_full(L[:64, :64].copy(), R[:64, :64].copy(), oracle.default_config(levels=3))  # spin up OpenMP
+        t0 = time.perf_counter()
+        oracle.match_full(L, R)
+        rate = pixel_iterations(480, 640) / (time.perf_counter() - t0)  # small images under-use the cores: conservative
+        cands = [(4928, 3264), (2464, 1632), (1232, 816)]
+        self.w, self.h = cands[-1]
+        for cw, ch in cands:
+            if pixel_iterations(ch, cw) / rate <= target_seconds * 1.6:
+                self.w, self.h = cw, ch
+                break
+        self.pi = pixel_iterations(self.h, self.w)
+        self.L, self.R, _, _ = synth.make_pair(self.w, self.h, 0)
+
+    def sample(self):
+        t0 = time.perf_counter()
+        self.oracle.match_full(self.L, self.R)
+        t = time.perf_counter() - t0
+        t16 = t * PIXEL_ITERS_16MP / self.pi
+        return {
+            "value": 1.0 / t16, "unit": UNIT, "cores": self.cores, "kind": "port",
+            "sample": "oracle (scalar C + OpenMP port of the reference kernels) full-pyramid match of the same synthetic "
+                      "scene at %dx%d: %.2f s for %.2f M pixel-iterations, scaled by pixel-iterations to the 16 MP pair "
+                      "(131.43 M) -> %.1f s/pair" % (self.w, self.h, t, self.pi / 1e6, t16),
+            "seconds_sample": t, "seconds_per_pair_scaled": t16,
+        }
 
 
 def run_reference(args):
     """Reference arm: the path's CPU implementation on the host cores.  The reference has no CPU
     implementation of its own for this path (CUDA only; its one CPU file is the separable convolution),
-    so this is the oracle port, all host threads, on a bounded sample per step."""
+    so this is the oracle port, all host threads, one bounded sample per step; exactly --warmup + --steps samples,
+    sized so that the whole run stays within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    n = args.warmup + args.steps
+    arm = CpuArm(target_seconds=max(1.0, 150.0 / max(n, 1)))
     vals = []
     cb = None
-    for i in range(args.warmup + args.steps):
-        cb = cpu_sample(target_seconds=10.0)
+    for i in range(n):
+        cb = arm.sample()
         if i >= args.warmup:
             vals.append(cb["seconds_per_pair_scaled"])
-        if sum(vals) and time.perf_counter() - T_START > 240:
-            break
     sec = sum(vals) / len(vals)
     val = 1.0 / sec
     cb["value"] = val
@@ -168,7 +210,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": val / 0.1, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm: bounded sample per step, scaled by pixel-iterations"},
+        "config": workload_config(),
+        "run": {"note": "CPU arm: one bounded sample per step, scaled by pixel-iterations", "seconds": time.perf_counter() - T_START},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -230,7 +273,8 @@ def run_gpu(args):
     devL = [t.to(dev) for t in hostL]
     devR = [t.to(dev) for t in hostR]
     step_bytes = COLS * 3
-    handles = [capi.Handle(device=local) for _ in range(NF)]
+    handles = [capi.Handle(device=local) for _ in range(NF)]       # production setting: the whole pair replays from a graph
+    timed = capi.Handle(device=local, use_graph=2)                   # instrumented: level 0 on the stream, events per launch
     out = [[torch.empty((ROWS, COLS), dtype=torch.float32, device=dev) for _ in range(3)] for _ in range(NF)]
     hout = [[torch.empty((ROWS, COLS), dtype=torch.float32, pin_memory=True) for _ in range(3)] for _ in range(NF)]
     stream = torch.cuda.current_stream()
@@ -240,21 +284,27 @@ def run_gpu(args):
         handles[k].match_full_device(devL[j].data_ptr(), devR[j].data_ptr(), ROWS, COLS, step_bytes,
                                      *[t.data_ptr() for t in out[k]])
 
+    def timed_step(k, i):
+        j = i % pool
+        timed.match_full_device(devL[j].data_ptr(), devR[j].data_ptr(), ROWS, COLS, step_bytes,
+                                *[t.data_ptr() for t in out[0]])
+
     def host_step(k, i):
         j = (i + k) % pool
         handles[k].match_full(hostL[j].numpy(), hostR[j].numpy(), out=tuple(t.numpy() for t in hout[k]))
 
-    def region(step_fn, nflight, steps):
+    def region(step_fn, nflight, steps, hs=None):
         """`steps` steps; one step = `nflight` pairs, one per handle, issued from one host thread each.
         Every call is synchronous on its own stream, so when the threads join all device work is done;
         timed with CUDA events on the current stream, max over ranks."""
         launches = [0] * nflight
         k1 = [0.0] * nflight
+        hs = hs or handles
 
         def work(k):
             for i in range(steps):
                 step_fn(k, i)
-                t = handles[k].timing()
+                t = hs[k].timing()
                 launches[k] += t.launches
                 k1[k] += t.k1_ms[0]
 
@@ -283,12 +333,34 @@ def run_gpu(args):
     # ---- C. one pair in flight: latency per pair and the clean per-launch K1 timing (roofline) ----
     # (bracketed by cudaProfilerStart/Stop so that `ncu --profile-from-start off` instruments exactly this
     # region: one launch list per pair without slowing the other ~10k launches of the run down)
+    lat_ms, _, _ = region(dev_step, 1, args.steps)
+    region(timed_step, 1, 2, [timed])
     torch.cuda.profiler.start()
-    lat_ms, _, k1_sum = region(dev_step, 1, args.steps)
+    _, _, k1_sum = region(timed_step, 1, args.steps, [timed])
     torch.cuda.profiler.stop()
     k1_avg = k1_sum / (2 * args.steps)  # level 0 runs 2 iterations (MatchGPULib.cpp:1741)
-    last = handles[0].timing()
+    last = timed.timing()
     e2e_lat_ms, _, _ = region(host_step, 1, max(3, args.steps // 2))
+
+    # ---- D. BASELINE configs[3]: the same pair in foveated mode (615x407 fovea on levels 0..5), one pair in flight ----
+    fd = capi.query_dims(capi.default_config(), ROWS, COLS, 1)
+    fstack = [torch.empty((fd.stack_rows, fd.fov_width), dtype=torch.float32, device=dev) for _ in range(3)]
+    fovh = capi.Handle(device=local)
+
+    def fov_dev_step(k, i):
+        j = i % pool
+        fovh.match_foveated_device(devL[j].data_ptr(), devR[j].data_ptr(), ROWS, COLS, step_bytes,
+                                   *[t.data_ptr() for t in fstack])
+
+    def fov_host_step(k, i):
+        j = i % pool
+        fovh.match_foveated(hostL[j].numpy(), hostR[j].numpy())
+
+    region(fov_dev_step, 1, 3, [fovh])
+    fov_ms, fov_launches, _ = region(fov_dev_step, 1, args.steps, [fovh])
+    region(fov_host_step, 1, 2, [fovh])
+    fov_e2e_ms, _, _ = region(fov_host_step, 1, max(3, args.steps // 2), [fovh])
+    fov_k1_ms = fovh.bench_correlate(fd.fov_width, fd.fov_height, 20)
     clocks = sampler.stop()
 
     # result sanity (not parity: tests/ do that): finite and close to the synthetic ground truth
@@ -301,28 +373,38 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = _peaks()
         ach = K1_BYTES_PER_PIXEL * COLS * ROWS / (k1_avg * 1e-3) / 1e9 if k1_avg > 0 else 0.0
-        cb = cpu_sample() if (world == 1 and not args.no_cpu_baseline) else None
+        cb = CpuArm(20.0).sample() if (world == 1 and not args.no_cpu_baseline) else None
         value = dp.throughput(NF, world, ms_step)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": value / 0.1,  # 10 s/pair = 0.1 pairs/s (GTX-class GPU, README.md:15)
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": NF,
-                       "parallelism": "pair-level data parallel x%d GPUs, %d pairs in flight per GPU (one handle + stream each)" % (world, NF),
-                       "l2": "inputs larger than L2: per-pair working set ~2.3 GB vs 126 MB L2; a pool of %d distinct pairs per GPU is cycled" % pool,
-                       "levels": 14, "pixel_iterations": PIXEL_ITERS_16MP, "sanity_epe_h_px": epe, "finite": finite,
-                       "ms_per_pair_latency_device": lat_ms, "ms_per_pair_latency_e2e": e2e_lat_ms},
+            "config": workload_config(),
+            "run": {"pairs_per_step_per_gpu": NF,
+                    "parallelism": "pair-level data parallel x%d GPUs, %d pairs in flight per GPU (one handle + stream each)" % (world, NF),
+                    "l2": "inputs larger than L2: per-pair working set ~2.5 GB vs 126 MB L2; a pool of %d distinct pairs per GPU is cycled" % pool,
+                    "sanity_epe_h_px": epe, "finite": finite,
+                    "ms_per_pair_latency_device": lat_ms, "ms_per_pair_latency_e2e": e2e_lat_ms},
             "e2e": {"value": dp.throughput(NF, world, e2e_ms_step), "unit": UNIT, "ms_per_step": e2e_ms_step,
                     "h2d_bytes_per_step": NF * 2 * ROWS * step_bytes, "d2h_bytes_per_step": NF * 3 * ROWS * COLS * 4},
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
-            "roofline": {"bound": "hbm", "kernel": "k1_correlate (fused warp+correlation+fit) at level 0, 4928x3264",
+            "foveated": {"workload": "16MP synthetic RGB pair, foveated mode, 615x407 fovea on levels 0..5 (BASELINE configs[3])",
+                         "ms_per_pair_device": fov_ms, "ms_per_pair_e2e": fov_e2e_ms, "pairs_in_flight": 1,
+                         "gpu_launches_per_pair": int(fov_launches // max(args.steps, 1)),
+                         "pixel_iterations": int(fd.pixel_iterations),
+                         "roofline": {"bound": "hbm", "kernel": "K1 at the fovea size %dx%d (the launch-bound levels: 12 of the 14 run at or below it)" % (fd.fov_width, fd.fov_height),
+                                      "avg_launch_ms": fov_k1_ms,
+                                      "achieved": K1_BYTES_PER_PIXEL * fd.fov_width * fd.fov_height / (fov_k1_ms * 1e-3) / 1e9,
+                                      "peak": peak, "unit": "GB/s",
+                                      "frac": K1_BYTES_PER_PIXEL * fd.fov_width * fd.fov_height / (fov_k1_ms * 1e-3) / 1e9 / peak}},
+            "roofline": {"bound": "hbm", "kernel": "K1 = k1_stream (fused warp + correlation + fit + confidence) at level 0, 4928x3264",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
                          "peak_source": peak_src, "avg_launch_ms": k1_avg,
                          "algorithmic_bytes_per_launch": K1_BYTES_PER_PIXEL * COLS * ROWS, "traffic": None,
-                         "timed_in": "the one-pair-in-flight region (CUDA events around every level-0 K1 launch)"},
+                         "timed_in": "an instrumented handle, one pair in flight (CUDA events around every level-0 K1 launch)"},
             "breakdown_ms": {"one_pair_in_flight_total": last.total_ms, "level0": last.level_ms[0],
                              "k1_level0_per_launch": last.k1_ms[0] / 2, "k2_level0_per_launch": last.k2_ms[0] / 2},
         }
@@ -343,11 +425,11 @@ def run_gpu(args):
                     line["roofline"]["issue_bound"] = {
                         "warp_instructions_per_launch": wi, "achieved_ginst_per_s": wi / (k1_avg * 1e-3) / 1e9,
                         "peak_ginst_per_s": peak_issue / 1e9, "frac": wi / (k1_avg * 1e-3) / peak_issue,
-                        "note": "secondary bound: the kernel executes 1185 instructions per pixel-iteration"}
+                        "note": "secondary bound: executed warp-instructions of the committed ncu capture over the live launch time"}
             except Exception:
                 pass
         emit_line(line)
-    for h in handles:
+    for h in handles + [timed, fovh]:
         h.close()
     if world > 1:
         dist.destroy_process_group()

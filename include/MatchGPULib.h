@@ -67,6 +67,7 @@ class MatchGPULib {
    private:
     ugsm_handle* h_;
     int device_;
+    int handle_fovea_level_ = 0;  // the foveatelevel the handle was created for
     char err_[512];
     bool ensure(int levels_unused = 0);
     float*** stackImpl(const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step, float*** lf,

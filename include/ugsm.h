@@ -57,7 +57,10 @@ typedef struct ugsm_config {
     int32_t smooth_passes;      /* smoothtime=5, MatchGPULib.cpp:38 */
     int32_t smooth_passes_fine; /* 10 on the two finest levels, MatchGPULib.cpp:2259-2261 */
     int32_t max_iters;          /* 0 = reference schedule; >0 caps iterations per level (tests only) */
-    int32_t use_graph;          /* 1 = replay the per-pair launch sequence through a CUDA graph; 0 = plain stream launches */
+    int32_t use_graph;          /* 1 = replay the per-pair launch sequence through a CUDA graph (default); 0 = plain
+                                   stream launches with per-level / per-launch timing; 2 = graph for levels >= 1, level
+                                   0 launched on the stream with timing events around its K1 / K2 launches
+                                   (instrumentation: ugsm_timing.k1_ms[0], k2_ms[0], level_ms[0]) */
 } ugsm_config;
 
 typedef struct ugsm_dims {
@@ -80,7 +83,7 @@ typedef struct ugsm_timing {
     float levels_ms;     /* coarse-to-fine loop (0 when replayed from a graph) */
     float h2d_ms, d2h_ms;
     int32_t launches;    /* kernels launched by the last call */
-    float level_ms[UGSM_MAX_LEVELS]; /* with use_graph only level 0 is outside the graph and timed */
+    float level_ms[UGSM_MAX_LEVELS]; /* use_graph 0: every level; 2: level 0 only; 1: none (all inside the graph) */
     /* Sum of the K1 (correlate) / K2 (smooth) launch durations per level, from CUDA events
      * recorded around every launch on the handle's stream; measured on the UGSM_TIMED_LEVELS
      * finest levels only (the others stay 0 so that events never pace the tiny kernels). */
@@ -109,7 +112,10 @@ int ugsm_set_stream(ugsm_handle* h, void* cuda_stream);
 /* mode: 0 = full pyramid, 1 = foveated.  Pure host arithmetic. */
 int ugsm_query_dims(const ugsm_config* cfg, int rows, int cols, int mode, ugsm_dims* out);
 
-/* Full-pyramid match.  Host buffers (pinned or pageable).  H, V, C: rows*cols floats each. */
+/* Full-pyramid match.  Host buffers (pinned or pageable).  H, V, C: rows*cols floats each.  An output plane that
+ * is not wanted may be NULL (here and in ugsm_match_foveated / ugsm_match_composite): it is not copied back -- e.g.
+ * H and V only, or nothing at all when the consumer is ugsm_cloud_from_match / ugsm_get_level_disparity, which read
+ * the planes the match left in device memory. */
 int ugsm_match_full(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step,
                     float* H, float* V, float* C);
 

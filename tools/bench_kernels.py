@@ -2,7 +2,7 @@ import os, sys, time
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import numpy as np
 from ug_stereomatcher_b200 import capi, synth
-h = capi.Handle()
+h = capi.Handle(use_graph=2)  # level 0 outside the graph: per-launch K1 / K2 times
 for (w, hh) in [(4928, 3264), (2463, 1631), (870, 576), (615, 407), (216, 142), (53, 34)]:
     print("%5dx%-5d K1 %.4f ms  K2(S5) %.4f ms  K2(S10) %.4f ms" % (w, hh, h.bench_correlate(w, hh, 5), h.bench_smooth(w, hh, 5, 5), h.bench_smooth(w, hh, 10, 5)))
 if os.environ.get("PAIR", "1") == "1":

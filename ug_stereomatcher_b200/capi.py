@@ -251,6 +251,11 @@ class Handle:
         if out is None:
             out = tuple(np.empty((rows, cols), np.float32) for _ in range(3))
         H, V, Cc = out
+        for a in out:  # the library writes rows*cols floats through each pointer: a mismatch corrupts host memory
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.shape == (rows, cols)
+                                      and a.flags.c_contiguous and a.flags.writeable):
+                raise UgsmError(ERR_INVALID, "out planes must be writable C-contiguous float32 arrays of shape "
+                                             "(rows, cols) or None")
         self._ck(lib().ugsm_match_full(self._h, _p(rgbL), _p(rgbR), rows, cols, rgbL.strides[0], _p(H), _p(V), _p(Cc)))
         return H, V, Cc
 

@@ -49,7 +49,13 @@ void MatchGPULib::gaussiankernel(float* k) {  // MatchGPULib.cpp:761-775
 }
 
 bool MatchGPULib::ensure(int) {
+    // foveatelevel is a public field of the reference class: a handle created for another value is replaced
+    if (h_ && handle_fovea_level_ != foveatelevel) {
+        ugsm_destroy(h_);
+        h_ = nullptr;
+    }
     if (h_) return true;
+    handle_fovea_level_ = foveatelevel;
     ugsm_config cfg;
     ugsm_config_default(&cfg);
     cfg.fovea_level = foveatelevel;
@@ -114,11 +120,8 @@ float*** MatchGPULib::stackImpl(const uint8_t* rgbL, const uint8_t* rgbR, int ro
     }
     fovW = d.fov_width;  // MatchGPULib.cpp:1233-1234
     fovH = d.fov_height;
-    size_t sn = (size_t)d.stack_rows * d.fov_width;
-    float* s[3];
-    for (int k = 0; k < 3; k++) s[k] = (float*)malloc(sn * sizeof(float));
-    int rc = ugsm_match_foveated(h_, rgbL, rgbR, rows, cols, step, s[0], s[1], s[2], nullptr, nullptr);
-    for (int k = 0; k < 3; k++) free(s[k]);  // per-level planes are fetched below at their own dims
+    // no stack planes requested: the per-level planes are fetched below at their own dims, once
+    int rc = ugsm_match_foveated(h_, rgbL, rgbR, rows, cols, step, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (rc != UGSM_OK) {
         snprintf(err_, sizeof err_, "%s", ugsm_last_error(h_));
         fprintf(stderr, "MatchGPULib: %s\n", err_);

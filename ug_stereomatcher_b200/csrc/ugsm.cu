@@ -28,6 +28,7 @@
 
 #include "ugsm_kernels.cuh"
 #include "ugsm_k1_stream.cuh"
+#include "ugsm_k2_stream.cuh"
 
 using namespace ugsm;
 
@@ -35,7 +36,9 @@ using namespace ugsm;
 
 namespace {
 
-std::string g_create_error;
+// Error text of calls that have no handle (ugsm_create, ugsm_host_alloc): per thread, so that handles created from
+// several threads (ugsm_batch: one handle per worker) neither race on it nor read a dangling pointer.
+thread_local char g_create_error[512] = "";
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
@@ -92,6 +95,11 @@ struct ugsm_handle {
     int k1s_min_seg = 32;     // shortest row segment of a strip (UGSM_K1S_MIN_SEG)
     int* d_flags = nullptr;   // per level: nonzero when the six matcher planes lie in [1, 256] (k1_stream FAST march)
     int k1_fast = 1;          // UGSM_K1_FAST=0: always take the guarded GENERIC march
+    int k2_stream = 1;        // large levels use the row pipeline k2_stream (UGSM_K2_STREAM=0: the tiled k2_smooth_box)
+    int k2s_slots[K2S_MAX_PASSES + 1] = {};  // co-resident k2_stream CTAs on the device per pass count
+    int k2s_min_seg = 48;     // shortest row segment of a strip (UGSM_K2S_MIN_SEG)
+    long k2s_min_pixels = 1500000;  // k2_stream runs levels of at least this many pixels (UGSM_K2S_MIN_PIXELS) ...
+    int k2s_max_passes = 6;         // ... and at most this many smoothing passes (UGSM_K2S_MAX_PASSES)
     long k1_small_pixels = 400000;  // levels below this use k1_correlate_small (UGSM_K1_SMALL_PIXELS)
     long k2_small_pixels = 700000;  // levels below this use k2_smooth_box_small (UGSM_K2_SMALL_PIXELS)
     int k0_rows_dense = 16, k0_rows_dec = 8;  // output rows per warp of k0_march5 (UGSM_K0_ROWS_DENSE / _DEC)
@@ -129,10 +137,14 @@ int fail(ugsm_handle* h, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (h)
-        h->err = buf;
-    else
-        g_create_error = buf;
+    if (h) {
+        try {
+            h->err = buf;
+        } catch (...) {  // out of memory while recording an error: keep the code, drop the text
+        }
+    } else {
+        snprintf(g_create_error, sizeof g_create_error, "%s", buf);
+    }
     return code;
 }
 
@@ -254,6 +266,20 @@ int set_kernel_attrs(ugsm_handle* h) {
     if (const char* e = getenv("UGSM_K0_ROWS_DEC")) h->k0_rows_dec = atoi(e) > 0 ? atoi(e) : h->k0_rows_dec;
     CK(cudaFuncSetAttribute(k2_smooth_box, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)k2_smem_bytes(K2_MAX_BH)));
+    if (const char* e = getenv("UGSM_K2_STREAM")) h->k2_stream = atoi(e);
+    if (const char* e = getenv("UGSM_K2S_MIN_SEG")) h->k2s_min_seg = atoi(e) > 0 ? atoi(e) : h->k2s_min_seg;
+    if (const char* e = getenv("UGSM_K2S_MIN_PIXELS")) h->k2s_min_pixels = atol(e);
+    if (const char* e = getenv("UGSM_K2S_MAX_PASSES")) h->k2s_max_passes = std::min(K2S_MAX_PASSES, std::max(0, atoi(e)));
+    CK(cudaFuncSetAttribute(k2_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)k2s_smem_bytes(K2S_MAX_PASSES)));
+    CK(cudaFuncSetAttribute(k2_stream, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (int sps = 0; sps <= K2S_MAX_PASSES; sps++) {
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k2_stream, (sps + 2) * 32, k2s_smem_bytes(sps)));
+        h->k2s_slots[sps] = std::max(1, nb) * h->sm_count;
+    }
+    if (const char* e = getenv("UGSM_K2S_SLOTS"))
+        for (int sps = 0; sps <= K2S_MAX_PASSES; sps++) h->k2s_slots[sps] = atoi(e) > 0 ? atoi(e) : h->k2s_slots[sps];
     h->k_attr_set = true;
     return UGSM_OK;
 }
@@ -318,6 +344,22 @@ void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci
         return;
     }
     p.hpad = align_up(R, 4);
+    if (h->k2_stream && passes <= h->k2s_max_passes && (long)w * hh >= h->k2s_min_pixels) {
+        // S <= 6 on levels of 1.5 MP and more: row pipeline over the passes (k2_stream), row segments sized for one
+        // co-resident wave.  (At S = 10 its 12-warp CTA is alone on an SM and the tiled kernel wins; measured.)
+        K2StreamParams sp;
+        sp.k = p;
+        sp.k.th = 0;
+        const int strips = div_up(w, K2_BW - 2 * p.hpad);
+        const int brows = y_end - y_begin;
+        int nseg = std::max(1, h->k2s_slots[passes] / strips);
+        nseg = std::min(nseg, std::max(1, brows / h->k2s_min_seg));
+        sp.seg_rows = div_up(brows, nseg);
+        dim3 grid(strips, div_up(brows, sp.seg_rows));
+        k2_stream<<<grid, (passes + 2) * 32, k2s_smem_bytes(passes), h->stream>>>(sp);
+        h->launches++;
+        return;
+    }
     const int twu = K2_BW - 2 * p.hpad;
     // Tile height: as tall as shared memory allows on big levels (less halo redundancy); shorter on
     // small levels so that there are at least ~2 CTAs per SM.
@@ -646,9 +688,11 @@ int run_pair(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int r
         rc = run_levels(h, levels - 1, 0, true);
         if (rc) return rc;
     } else {
-        // Graph: pyramid + crops/energy + levels [levels-1 .. 1] (hundreds of short launches, where the
-        // ~4 us launch floor matters).  Level 0 (ms-long kernels) stays outside so that its K1/K2
-        // launches keep their timing events.
+        // Graph: pyramid + crops/energy + the whole coarse-to-fine loop (hundreds of short launches, where the
+        // ~4 us launch floor matters).  use_graph == 2 (instrumentation: bench.py's roofline region, tools/) keeps
+        // level 0 outside the graph so that its K1 / K2 launches get timing events; production (1) does not pay
+        // for that.
+        const int graph_lo = (h->cfg.use_graph == 2) ? 1 : 0;
         if (!h->graph_exec) {
             // Capture once per shape: every buffer the sequence touches belongs to the handle's arena.
             const int l0 = h->launches;
@@ -656,7 +700,7 @@ int run_pair(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int r
             CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
             build_pyramid(h, 2);
             prepare_levels(h);
-            rc = run_levels(h, levels - 1, 1, false);
+            rc = run_levels(h, levels - 1, graph_lo, false);
             cudaError_t e = cudaStreamEndCapture(h->stream, &g);
             if (rc || e != cudaSuccess || !g) {
                 if (g) cudaGraphDestroy(g);
@@ -673,9 +717,11 @@ int run_pair(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int r
         }
         CK(cudaGraphLaunch(h->graph_exec, h->stream));
         h->launches += h->graph_launches;
-        CK(cudaEventRecord(h->ev[4 + 1], h->stream));
-        rc = run_levels(h, 0, 0, true);
-        if (rc) return rc;
+        if (graph_lo == 1) {
+            CK(cudaEventRecord(h->ev[4 + 1], h->stream));
+            rc = run_levels(h, 0, 0, true);
+            if (rc) return rc;
+        }
     }
     CK(cudaEventRecord(h->ev[2], h->stream));
     CK(cudaGetLastError());
@@ -695,7 +741,8 @@ int finish_timing(ugsm_handle* h) {
     t.pyramid_ms = t.levels_ms = 0.f;
     for (int i = 0; i < UGSM_MAX_LEVELS; i++) t.level_ms[i] = t.k1_ms[i] = t.k2_ms[i] = 0.f;
     const int levels = h->cfg.levels;
-    const bool graph = h->cfg.use_graph && levels >= 2;  // then only level 0 has inner events
+    const bool graph = h->cfg.use_graph && levels >= 2;  // then at most level 0 has inner events
+    if (graph && h->cfg.use_graph != 2) return UGSM_OK;  // everything replayed from the graph: only the total
     float v = 0;
     if (!graph) {
         CK(cudaEventElapsedTime(&v, h->ev[0], h->ev[1]));
@@ -742,7 +789,8 @@ int ensure_staging(ugsm_handle* h, size_t rgb_bytes, size_t out_floats) {
 // Write the results of the last run_pair into dense device planes.
 int emit_full(ugsm_handle* h, float* dH, float* dV, float* dC) {
     LevelBuf& b = h->lv[0];
-    launch_copy3(h, b.st[0], b.st[1], b.st[2], b.mpitch, dH, dV, dC, b.mw, b.mw, b.mh);
+    launch_copy3(h, dH ? b.st[0] : nullptr, dV ? b.st[1] : nullptr, dC ? b.st[2] : nullptr, b.mpitch, dH, dV, dC, b.mw,
+                 b.mw, b.mh);
     CK(cudaGetLastError());
     return UGSM_OK;
 }
@@ -1131,8 +1179,9 @@ int ugsm_create(const ugsm_config* cfg, ugsm_handle** out) {
     if (prop.major != 10)
         return fail(nullptr, UGSM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
                     prop.major, prop.minor);
-    if (const char* e = getenv("UGSM_USE_GRAPH")) c.use_graph = atoi(e) ? 1 : 0;  // override for profiling runs
-    h = new ugsm_handle();
+    if (const char* e = getenv("UGSM_USE_GRAPH")) c.use_graph = std::min(2, std::max(0, atoi(e)));  // override for profiling runs
+    h = new (std::nothrow) ugsm_handle();
+    if (!h) return fail(nullptr, UGSM_ERR_NOMEM, "out of host memory");
     h->cfg = c;
     h->device = dev;
     h->sm_count = prop.multiProcessorCount;
@@ -1182,6 +1231,7 @@ int ugsm_destroy(ugsm_handle* h) {
         if (ev) cudaEventDestroy(ev);
     if (h->cloud_buf) cudaFree(h->cloud_buf);
     if (h->d_flags) cudaFree(h->d_flags);
+
     if (h->pin_in) cudaFreeHost(h->pin_in);
     if (h->pin_out) cudaFreeHost(h->pin_out);
     for (auto& ev : h->chunk_ev)
@@ -1191,7 +1241,7 @@ int ugsm_destroy(ugsm_handle* h) {
     return UGSM_OK;
 }
 
-const char* ugsm_last_error(const ugsm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+const char* ugsm_last_error(const ugsm_handle* h) { return h ? h->err.c_str() : g_create_error; }
 
 int ugsm_set_stream(ugsm_handle* h, void* cuda_stream) {
     if (!h) return UGSM_ERR_INVALID;
@@ -1234,7 +1284,10 @@ int ugsm_match_foveated_device(ugsm_handle* h, const uint8_t* d_rgbL, const uint
 static int match_host(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, int rows, int cols, size_t step,
                       int mode, float* o0, float* o1, float* o2, int* fovW, int* fovH) {
     if (!h) return UGSM_ERR_INVALID;
-    if (!rgbL || !rgbR || !o0 || !o1 || !o2) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+    if (!rgbL || !rgbR) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+    // an output plane the caller does not want is NULL: it is neither converted nor copied back (all three NULL:
+    // the results stay on the device for ugsm_get_level_disparity / ugsm_cloud_from_match)
+    const bool want_any = o0 || o1 || o2;
     if (rows < 1 || cols < 1 || step < (size_t)cols * 3) return fail(h, UGSM_ERR_INVALID, "bad rows/cols/step");
     const bool composite = (mode == 2);
     if (composite) mode = 1;
@@ -1242,18 +1295,20 @@ static int match_host(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, 
     int rc = compute_dims(h->cfg, rows, cols, mode, &d);
     if (rc) return fail(h, rc, "invalid shape/config: rows=%d cols=%d mode=%d", rows, cols, mode);
     CK(cudaSetDevice(h->device));
-    size_t rgb_bytes = step * (size_t)rows;
+    // a strided view (cv::Mat ROI, step > cols*3) ends cols*3 bytes into its last row: never touch the rest
+    size_t rgb_bytes = step * (size_t)(rows - 1) + (size_t)cols * 3;
     size_t out_floats = (mode == 0 || composite) ? (size_t)rows * cols : (size_t)d.stack_rows * d.fov_width;
-    rc = ensure_staging(h, rgb_bytes, out_floats);
+    rc = ensure_staging(h, rgb_bytes, want_any ? out_floats : 1);
     if (rc) return rc;
     float* outs[3] = {o0, o1, o2};
     const HostXfer xin[2] = {{rgbL, h->d_rgb[0], rgb_bytes}, {rgbR, h->d_rgb[1], rgb_bytes}};
-    const HostXfer xout[3] = {{h->d_out[0], o0, out_floats * sizeof(float)},
-                              {h->d_out[1], o1, out_floats * sizeof(float)},
-                              {h->d_out[2], o2, out_floats * sizeof(float)}};
-    const bool stage_in = want_staging(h, xin, 2, true), stage_out = want_staging(h, xout, 3, false);
+    HostXfer xout[3];
+    int nout = 0;
+    for (int k = 0; k < 3; k++)
+        if (outs[k]) xout[nout++] = HostXfer{h->d_out[k], outs[k], out_floats * sizeof(float)};
+    const bool stage_in = want_staging(h, xin, 2, true), stage_out = nout > 0 && want_staging(h, xout, nout, false);
     if (stage_in || stage_out) {
-        rc = ensure_pinned(h, stage_in ? staged_bytes(xin, 2) : 0, stage_out ? staged_bytes(xout, 3) : 0);
+        rc = ensure_pinned(h, stage_in ? staged_bytes(xin, 2) : 0, stage_out ? staged_bytes(xout, nout) : 0);
         if (rc) return rc;
     }
     CK(cudaEventRecord(h->ev[3], h->stream));
@@ -1270,18 +1325,19 @@ static int match_host(ugsm_handle* h, const uint8_t* rgbL, const uint8_t* rgbR, 
         rc = run_composite(h);
         if (rc) return rc;
         CK(cudaEventRecord(h->ev[2], h->stream));  // the composite belongs to the pair's device time
-        rc = emit_composite(h, h->d_out[0], h->d_out[1], h->d_out[2]);
-    } else {
-        rc = mode == 0 ? emit_full(h, h->d_out[0], h->d_out[1], h->d_out[2])
+        if (want_any) rc = emit_composite(h, h->d_out[0], h->d_out[1], h->d_out[2]);
+    } else if (want_any) {
+        rc = mode == 0 ? emit_full(h, o0 ? h->d_out[0] : nullptr, o1 ? h->d_out[1] : nullptr, o2 ? h->d_out[2] : nullptr)
                        : emit_stack(h, h->d_out[0], h->d_out[1], h->d_out[2]);
     }
     if (rc) return rc;
     if (stage_out) {
-        rc = staged_d2h(h, xout, 3);
+        rc = staged_d2h(h, xout, nout);
         if (rc) return rc;
     } else {
         for (int k = 0; k < 3; k++)
-            CK(cudaMemcpyAsync(outs[k], h->d_out[k], out_floats * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+            if (outs[k])
+                CK(cudaMemcpyAsync(outs[k], h->d_out[k], out_floats * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
     rc = finish_timing(h);
@@ -1356,7 +1412,7 @@ int ugsm_host_alloc(size_t bytes, void** out) {
     cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        g_create_error = std::string("ugsm_host_alloc: ") + cudaGetErrorString(e);
+        snprintf(g_create_error, sizeof g_create_error, "ugsm_host_alloc: %s", cudaGetErrorString(e));
         *out = nullptr;
         return e == cudaErrorMemoryAllocation ? UGSM_ERR_NOMEM : UGSM_ERR_NO_DEVICE;
     }
@@ -1409,7 +1465,7 @@ static int cloud_host(ugsm_handle* h, const ugsm_camera_pair* cam, const float* 
     uint8_t* d_img = reinterpret_cast<uint8_t*>(base + 2 * plane);
     float* d_pts = reinterpret_cast<float*>(base + 2 * plane + img_bytes);
     const size_t plane_bytes = (size_t)rows * cols * sizeof(float);
-    const HostXfer xin[3] = {{X, dX, plane_bytes}, {Y, dY, plane_bytes}, {img, d_img, step * (size_t)im_rows}};
+    const HostXfer xin[3] = {{X, dX, plane_bytes}, {Y, dY, plane_bytes}, {img, d_img, step * (size_t)(im_rows - 1) + (size_t)im_cols * 3}};
     const HostXfer xout[1] = {{d_pts, points, pts_bytes}};
     const bool stage_in = want_staging(h, xin, 3, true), stage_out = want_staging(h, xout, 1, false);
     if (stage_in || stage_out) {
@@ -1448,6 +1504,12 @@ int ugsm_cloud_foveated(ugsm_handle* h, const ugsm_camera_pair* cam, const float
     if (!stackH || !stackV) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
     if (src_level < 0 || src_level >= h->cfg.fovea_level || fov_rows < 1 || fov_cols < 1)
         return fail(h, UGSM_ERR_INVALID, "src_level %d outside the stack", src_level);
+    // the kernel maps fovea coordinates into the image through the level geometry: a fovea of any other size would
+    // read the image out of bounds (a sticky device fault for every handle of the process)
+    ugsm_dims d;
+    if (compute_dims(h->cfg, im_rows, im_cols, 1, &d) != UGSM_OK || fov_cols != d.fov_width || fov_rows != d.fov_height)
+        return fail(h, UGSM_ERR_INVALID, "fovea %dx%d does not match the %dx%d image at fovea level %d", fov_cols,
+                    fov_rows, im_cols, im_rows, h->cfg.fovea_level);
     const size_t off = (size_t)src_level * fov_rows * fov_cols;  // PC:900: row yy + fovH * srcLevel
     return cloud_host(h, cam, stackH + off, stackV + off, fov_rows, fov_cols, src_level, im_rows, im_cols, img, step,
                       bgr, sampling, points, point_stride, npoints);
@@ -1562,9 +1624,10 @@ int ugsm_stage_pyramid(ugsm_handle* h, const uint8_t* rgb, int rows, int cols, s
     CK(cudaSetDevice(h->device));
     int rc = prepare_shape(h, rows, cols, 0);
     if (rc) return rc;
-    rc = ensure_staging(h, step * (size_t)rows, 1);
+    const size_t rgb_bytes = step * (size_t)(rows - 1) + (size_t)cols * 3;  // the last row ends after cols*3 bytes
+    rc = ensure_staging(h, rgb_bytes, 1);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->d_rgb[0], rgb, step * (size_t)rows, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_rgb[0], rgb, rgb_bytes, cudaMemcpyHostToDevice, h->stream));
     unpack_images(h, h->d_rgb[0], nullptr, step);
     build_pyramid(h, 1);
     CK(cudaGetLastError());
