@@ -6,8 +6,11 @@
 // and written out so that tests/test_gpu_node.py can compare them with the C-ABI results.
 //
 //   refnode <in.bin> <out.bin> [node args...]      (node args: argv[2] = fovea level, as the node takes it)
-//   in : int32 foveated(0/1), rows, cols; uint8 rgbL[rows*cols*3], rgbR[rows*cols*3]
-//   out: for each topic in a fixed order: int32 rows, cols; float data[rows*cols]   (rows = 0: not published)
+//   in : int32 mode, rows, cols; uint8 rgbL[rows*cols*3], rgbR[rows*cols*3]
+//        mode bit 0 = the node's `foveated` parameter; bit 1 = go through the service callback disparitySrv
+//        (UG_GPU_matcher.cpp:497-690, srv/GetDisparitiesGPU.srv) instead of the topic callback mainRoutine
+//   out: for each topic, then for each response field of the service, in a fixed order:
+//        int32 rows, cols; float data[rows*cols]   (rows = 0: not published / not filled)
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -39,7 +42,7 @@ int main(int argc, char** argv) {
     if (!f) return 2;
     int32_t hd[3];
     rd(f, hd, sizeof hd);
-    const int foveated = hd[0], rows = hd[1], cols = hd[2];
+    const int foveated = hd[0] & 1, service = (hd[0] >> 1) & 1, rows = hd[1], cols = hd[2];
     sensor_msgs::Image* imL = new sensor_msgs::Image;
     sensor_msgs::Image* imR = new sensor_msgs::Image;
     imL->payload = cv::Mat(rows, cols, CV_8UC3);
@@ -57,7 +60,18 @@ int main(int argc, char** argv) {
     nargv.push_back(argv[0]);
     for (int i = 3; i < argc; i++) nargv.push_back(argv[i]);
     GPU_matcher node((int)nargv.size(), nargv.data());
-    node.mainRoutine(sensor_msgs::ImageConstPtr(imL), sensor_msgs::ImageConstPtr(imR));
+    ug_stereomatcher::GetDisparitiesGPU::Request req;
+    ug_stereomatcher::GetDisparitiesGPU::Response rsp;
+    if (service) {
+        req.imL = *imL;
+        req.imR = *imR;
+        if (!node.disparitySrv(req, rsp)) {
+            fprintf(stderr, "refnode: disparitySrv returned false\n");
+            return 3;
+        }
+    } else {
+        node.mainRoutine(sensor_msgs::ImageConstPtr(imL), sensor_msgs::ImageConstPtr(imR));
+    }
 
     static const char* topics[] = {"output_disparityH", "output_disparityV", "output_disparityC", "output_stackH",
                                    "output_stackV",     "output_stackC",     "output_stackL_pyramid",
@@ -73,6 +87,14 @@ int main(int argc, char** argv) {
         }
         fwrite(dims, sizeof dims, 1, o);
         if (dims[0] > 0) fwrite(it->second.data, 4, (size_t)dims[0] * dims[1], o);
+    }
+    // GetDisparitiesGPU response: dispH, dispV, dispC (.image), fdispH, fdispV, fdispC (.image_stack)
+    const cv::Mat* fields[6] = {&rsp.dispH.image.payload,       &rsp.dispV.image.payload,       &rsp.dispC.image.payload,
+                                &rsp.fdispH.image_stack.payload, &rsp.fdispV.image_stack.payload, &rsp.fdispC.image_stack.payload};
+    for (const cv::Mat* mt : fields) {
+        int32_t dims[2] = {mt->data ? mt->rows : 0, mt->data ? mt->cols : 0};
+        fwrite(dims, sizeof dims, 1, o);
+        if (dims[0] > 0) fwrite(mt->data, 4, (size_t)dims[0] * dims[1], o);
     }
     fclose(o);
     return 0;

@@ -3,8 +3,9 @@
 (oracle/_ref/refcuda, built by oracle/refbuild/Makefile from /root/reference through compat shims)
 run on a B200, on the synthetic pair synth.make_pair(1232, 816, 0), reference defaults (14 levels).
 
-Run on the GPU box:   python tests/golden/make_refcuda_golden.py gpurun_out
-It stores two 320x240 crops (one interior, one touching the top-left border) of H, V, C plus the
+Run on the GPU box:   python tests/golden/make_refcuda_golden.py gpurun_out [W H]
+(W H = 2464 1632 repeats the run at BASELINE configs[1]'s size: statistics and timings only,
+tests/golden/refcuda_2464x1632_stats.json).  It stores two 320x240 crops (one interior, one touching the top-left border) of H, V, C plus the
 full-frame agreement statistics against the oracle and against this repo's CUDA path, so the CPU
 test (tests/test_refcuda_golden.py) can pin the oracle without a GPU.
 """
@@ -24,7 +25,7 @@ W, H = 1232, 816
 CROPS = {"interior": (300, 450, 240, 320), "corner": (0, 0, 240, 320)}  # y0, x0, h, w
 
 
-def main(outdir):
+def main(outdir, W=W, H=H):
     import ugsm_oracle as oracle
     from ug_stereomatcher_b200 import capi, synth
 
@@ -72,11 +73,13 @@ def main(outdir):
     for name, (y0, x0, hh, ww) in CROPS.items():
         arrays[name] = out[:, y0:y0 + hh, x0:x0 + ww].copy()
     os.makedirs(outdir, exist_ok=True)
-    np.savez_compressed(os.path.join(outdir, "refcuda_1232x816.npz"), **arrays)
-    json.dump(st, open(os.path.join(outdir, "refcuda_1232x816_stats.json"), "w"), indent=1)
-    open(os.path.join(outdir, "refcuda_1232x816_log_tail.txt"), "w").write(log[-4000:])
+    tag = "refcuda_%dx%d" % (W, H)
+    if (W, H) == (1232, 816):
+        np.savez_compressed(os.path.join(outdir, tag + ".npz"), **arrays)
+    json.dump(st, open(os.path.join(outdir, tag + "_stats.json"), "w"), indent=1)
+    open(os.path.join(outdir, tag + "_log_tail.txt"), "w").write(log[-4000:])
     print(json.dumps(st, indent=1))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out")
+    main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out", *(int(a) for a in sys.argv[2:4]))

@@ -197,6 +197,31 @@ def test_16mp_full_and_foveated_bit_exact(capi, oracle):
     _cmp(fov[:3], (wH, wV, wC), "16MP foveated")
 
 
+def test_4mp_full_pyramid_bit_exact(capi, oracle):
+    """BASELINE configs[1] at its stated size: 2464x1632 (calibrations/calL.xml:5-6), full pyramid, reference
+    defaults, against the oracle bit for bit.  Also: the H + V only call (C not copied back) returns the same planes,
+    and a pair with black pixels (the levels' range flags clear on the device, K1 runs its guarded march) matches
+    the oracle as well."""
+    L, R, dH, dV = synth.make_pair(2464, 1632, 1)
+    with capi.Handle() as h:
+        got = h.match_full(L, R)
+        H2 = np.empty_like(got[0])
+        V2 = np.empty_like(got[1])
+        h.match_full(L, R, out=(H2, V2, None))
+    want = oracle.match_full(L, R)
+    _cmp(got, want, "4MP full")
+    assert np.array_equal(H2, got[0]) and np.array_equal(V2, got[1])
+    m = (slice(64, -64), slice(64, -64))
+    assert np.abs(got[0] - dH)[m].mean() < 0.35 and np.abs(got[1] - dV)[m].mean() < 0.35  # sanity EPE only
+    Lb, Rb = L.copy(), R.copy()
+    Lb[200:260, 300:420] = 0
+    Rb[700:705, :] = 0
+    Rb[1000:1100, 2000:2100] = 0
+    with capi.Handle() as h:
+        gotb = h.match_full(Lb, Rb)
+    _cmp(gotb, oracle.match_full(Lb, Rb), "4MP full with black regions")
+
+
 def test_pageable_staging_equals_plain_path(capi, monkeypatch):
     """Pageable host buffers of >= 8 MB go through pinned staging with copy threads (what a caller of the
     MatchGPULib facade gets): same bits as the plain cudaMemcpy path, with fresh and with reused output planes,

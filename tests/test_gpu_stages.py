@@ -172,6 +172,50 @@ def test_match_level_bit_exact_vs_live_reference_cuda(gpu, tmp_path):
             _assert_same(g, r, "%s %s vs live reference CUDA" % (name, n))
 
 
+@pytest.mark.parametrize("level,iters,passes", [(13, 2, 10), (11, 6, 5)])
+def test_large_kernels_bit_exact_vs_live_reference_cuda(capi, tmp_path, level, iters, passes):
+    """The LARGE-level kernels (k1_stream above 400 k pixels; the tiled k2_smooth_box at S = 10 and the pipelined
+    k2_stream at S = 5) against the UNMODIFIED reference CUDA code run live on the same GPU at 1024x768 (W % 128 = 0,
+    H % 64 = 0: no out-of-bounds accidents in the reference, 786 k pixels: above both switch points): the finest-level
+    schedule (reference level 13: 2 iterations, S = 10) and the third-finest (level 11: 6 iterations, S = 5, threshold
+    schedule), bit-exact with no oracle in between, in the FAST and in the GENERIC march of K1."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "refcuda_stage")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/refcuda_stage not built (reference checkout absent at build time)")
+    W, H = 1024, 768
+    L, R, dH, dV = synth.make_pair(W, H, 6)
+    L3, R3 = _planes(L), _planes(R)
+    rng = np.random.default_rng(31)
+    H0 = (0.8 * dH + rng.uniform(-0.3, 0.3, dH.shape)).astype(np.float32)
+    V0 = (0.8 * dV + rng.uniform(-0.3, 0.3, dV.shape)).astype(np.float32)
+    C0 = rng.uniform(0.4, 1.0, dH.shape).astype(np.float32)
+    fin, fout = str(tmp_path / "in.f32"), str(tmp_path / "out.f32")
+    np.concatenate([L3.ravel(), R3.ravel(), H0.ravel(), V0.ravel(), C0.ravel()]).astype(np.float32).tofile(fin)
+    p = subprocess.run([exe, "level", str(W), str(H), str(level), fin, fout], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, timeout=900)
+    assert p.returncode == 0, p.stdout.decode(errors="ignore")[-2000:]
+    ref = np.fromfile(fout, np.float32).reshape(3, H, W)
+    old = {k: os.environ.get(k) for k in ("UGSM_K1_FAST", "UGSM_K2S_MIN_PIXELS")}
+    try:
+        for fast in ("1", "0"):
+            os.environ["UGSM_K1_FAST"] = fast
+            os.environ["UGSM_K2S_MIN_PIXELS"] = "0"  # S = 5 at 786 k pixels: run the pipelined K2 as well
+            with capi.Handle() as h:
+                got = h.stage_match_level(L3, R3, H0, V0, C0, iters, passes, False)
+            for g, r, n in zip(got, ref, "HVC"):
+                _assert_same(g, r, "1024x768 level %d %s (K1 fast=%s) vs live reference CUDA" % (level, n, fast))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 def _assert_same_away_from_nonfinite(g, w, what):
     """Bit equality everywhere except within 2 px of a non-finite value: the oracle multiplies the box
     filter's zero outer taps (0 * NaN = NaN, MatchLib.cu:1616-1623), the CUDA kernel skips them.  State

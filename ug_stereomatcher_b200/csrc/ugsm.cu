@@ -95,6 +95,8 @@ struct ugsm_handle {
     int k1s_min_seg = 32;     // shortest row segment of a strip (UGSM_K1S_MIN_SEG)
     int* d_flags = nullptr;   // per level: nonzero when the six matcher planes lie in [1, 256] (k1_stream FAST march)
     int k1_fast = 1;          // UGSM_K1_FAST=0: always take the guarded GENERIC march
+    int k1_tma = 1;           // left image / U / C rows of k1_stream arrive as TMA tiles (UGSM_K1_TMA=0: cp.async)
+    void* tma_encode = nullptr;  // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint
     int k2_stream = 1;        // large levels use the row pipeline k2_stream (UGSM_K2_STREAM=0: the tiled k2_smooth_box)
     int k2s_slots[K2S_MAX_PASSES + 1] = {};  // co-resident k2_stream CTAs on the device per pass count
     int k2s_min_seg = 48;     // shortest row segment of a strip (UGSM_K2S_MIN_SEG)
@@ -253,10 +255,17 @@ int set_kernel_attrs(ugsm_handle* h) {
     if (const char* e = getenv("UGSM_K1_STREAM")) h->k1_stream = atoi(e);
     if (const char* e = getenv("UGSM_K1_FAST")) h->k1_fast = atoi(e);
     if (const char* e = getenv("UGSM_K1S_MIN_SEG")) h->k1s_min_seg = atoi(e) > 0 ? atoi(e) : h->k1s_min_seg;
+    if (const char* e = getenv("UGSM_K1_TMA")) h->k1_tma = atoi(e);
     {
-        CK(cudaFuncSetAttribute(k1_stream, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &h->tma_encode, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            h->tma_encode = nullptr;  // then k1_stream<false> (all cp.async) runs
+        cudaGetLastError();
+        CK(cudaFuncSetAttribute(k1_stream<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(k1_stream<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1_stream, K1S_NW * 32, K1S_NW * sizeof(K1Ring)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k1_stream<true>, K1S_NW * 32, K1S_NW * sizeof(K1Ring)));
         h->k1s_slots = std::max(1, nb) * h->sm_count;
         if (const char* e = getenv("UGSM_K1S_SLOTS")) h->k1s_slots = atoi(e) > 0 ? atoi(e) : h->k1s_slots;
     }
@@ -284,6 +293,23 @@ int set_kernel_attrs(ugsm_handle* h) {
     return UGSM_OK;
 }
 
+// 2-D f32 tensor map of a w x hh plane (row pitch `pitch` floats): tiles of box_w x box_h, zero fill outside the
+// image.  False when the plane cannot be described (base not 16-byte aligned, pitch not a multiple of 4 floats).
+bool make_plane_map(ugsm_handle* h, CUtensorMap* tm, const float* plane, int w, int hh, int pitch, int box_w, int box_h) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    if (!h->tma_encode || (reinterpret_cast<uintptr_t>(plane) & 15) || (pitch & 3)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)hh};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    return reinterpret_cast<encode_fn>(h->tma_encode)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(plane),
+                                                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 void launch_k1(ugsm_handle* h, const K1Params& p, const int* fast_flag = nullptr) {
     // Large levels: streaming strip march (k1_stream): one warp per 30-column strip and row segment; the
     // segment length is chosen so that all CTAs of the launch are co-resident (one wave, no tail).
@@ -300,7 +326,12 @@ void launch_k1(ugsm_handle* h, const K1Params& p, const int* fast_flag = nullptr
         nseg = std::min(nseg, std::max(1, band_rows / h->k1s_min_seg));
         sp.seg_rows = div_up(band_rows, nseg);
         dim3 grid(strips, div_up(band_rows, sp.seg_rows));
-        k1_stream<<<grid, K1S_NW * 32, K1S_NW * sizeof(K1Ring), h->stream>>>(sp);
+        bool tma = h->k1_tma != 0;
+        for (int k = 0; k < 3 && tma; k++) tma = make_plane_map(h, &sp.tm[k], p.L[k], p.w, p.h, p.pitch, K1S_LP, K1S_CH);
+        if (tma)
+            k1_stream<true><<<grid, K1S_NW * 32, K1S_NW * sizeof(K1Ring), h->stream>>>(sp);
+        else
+            k1_stream<false><<<grid, K1S_NW * 32, K1S_NW * sizeof(K1Ring), h->stream>>>(sp);
     } else if (big && h->k1_nw == 2) {
         dim3 grid(div_up(p.w, 60), div_up(band_rows, K1_TH));
         k1_correlate<2, K1_TH><<<grid, 64, sizeof(K1Smem<2, K1_TH>), h->stream>>>(p);
