@@ -226,6 +226,18 @@ int ugsm_band_unpack(ugsm_handle* h, int level, int y_begin, int y_end, const fl
 /* Copy rows [y_begin, y_end) of the level-0 result into dense (pitch == width) output planes. */
 int ugsm_band_emit(ugsm_handle* h, float* dH, float* dV, float* dC, int y_begin, int y_end);
 
+/* The same schedule driven from C++ inside the library (csrc/ugsm_rowband.cu): one pair split into row bands over
+ * n handles, one per GPU of the box (devices[r] = CUDA ordinal of handles[r]; several ranks on one device emulate
+ * the split on a single GPU).  One host thread per rank; halo rows travel straight from one GPU's level planes into
+ * its neighbour's (cudaMemcpy2DAsync over NVLink peer access, ordered by events), every rank writes its band of the
+ * result into the dense planes dH, dV, dC on devices[0].  d_rgbL[r] / d_rgbR[r]: the image pair resident on
+ * devices[r].  device_ms (may be NULL): time on rank 0's stream from the first launch to the assembled result.
+ * Bit-identical to ugsm_match_full_device.  Error text: ugsm_rowband_last_error(). */
+int ugsm_rowband_match(ugsm_handle* const* handles, const int* devices, int n, const uint8_t* const* d_rgbL,
+                       const uint8_t* const* d_rgbR, int rows, int cols, size_t step, int split_levels, float* dH,
+                       float* dV, float* dC, float* device_ms);
+const char* ugsm_rowband_last_error(void);
+
 const char* ugsm_version(void);
 
 /* ---- Point cloud from the disparity planes.  K5 replaces the per-pixel host loops of

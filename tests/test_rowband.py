@@ -53,3 +53,34 @@ def test_emulated_rowband_bit_exact(capi, world):
         assert (got == w_).all(), "row-band (world=%d) differs in %d px" % (world, int((got != w_).sum()))
     for hd in handles:
         hd.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
+def test_cpp_rowband_driver_bit_exact(capi, world):
+    """ugsm_rowband_match (csrc/ugsm_rowband.cu): the C++ driver -- one host thread per rank, halo rows copied straight
+    between the ranks' level planes, event-ordered streams -- with all ranks emulated on cuda:0 (same-device copies
+    instead of NVLink peer copies; the multi-GPU run is tools/rowband_bench.py / bench.py --mode rowband).  Two pairs
+    through the same handles (graph replay of the replicated part), bit-exact against the single-GPU path."""
+    import torch
+
+    rows, cols = 816, 1232
+    dev = torch.device("cuda", 0)
+    handles = [capi.Handle() for _ in range(world)]
+    out = [torch.empty((rows, cols), dtype=torch.float32, device=dev) for _ in range(3)]
+    for seed in (4, 5):
+        L, R, _, _ = synth.make_pair(cols, rows, seed)
+        dL, dR = torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev)
+        for o in out:
+            o.fill_(float("nan"))
+        torch.cuda.synchronize()
+        ms = capi.rowband_match(handles, [0] * world, [dL.data_ptr()] * world, [dR.data_ptr()] * world, rows, cols,
+                                cols * 3, [o.data_ptr() for o in out])
+        assert ms > 0
+        with capi.Handle() as h:
+            want = h.match_full(L, R)
+        for o, w_ in zip(out, want):
+            got = o.cpu().numpy()
+            assert (got == w_).all(), "C++ row-band (world=%d) differs in %d px" % (world, int((got != w_).sum()))
+    for hd in handles:
+        hd.close()

@@ -27,6 +27,7 @@ SYMBOLS = [
     "ugsm_band_level_info", "ugsm_band_iteration", "ugsm_band_upsample", "ugsm_band_emit", "ugsm_band_pack",
     "ugsm_band_unpack", "ugsm_cloud_count", "ugsm_cloud_full", "ugsm_cloud_full_device", "ugsm_cloud_foveated",
     "ugsm_cloud_from_match", "ugsm_cloud_last_ms", "ugsm_bench_pyramid", "ugsm_host_alloc", "ugsm_host_free",
+    "ugsm_rowband_match", "ugsm_rowband_last_error",
 ]
 
 
@@ -190,6 +191,24 @@ def cloud_count(rows, cols, sampling=1):
     if lib().ugsm_cloud_count(rows, cols, sampling, C.byref(n)) != OK:
         raise UgsmError(ERR_INVALID, "ugsm_cloud_count: invalid rows/cols/sampling")
     return n.value
+
+
+def rowband_match(handles, devices, d_rgbL, d_rgbR, rows, cols, step, out, split_levels=3):
+    """ugsm_rowband_match: one pair split into row bands over `handles` (one per GPU; device pointers as ints).
+    `out`: three device pointers (dense rows x cols planes on devices[0]).  Returns the device time in ms."""
+    n = len(handles)
+    hs = (C.c_void_p * n)(*[h._h for h in handles])
+    dv = (C.c_int * n)(*devices)
+    pl = (C.c_void_p * n)(*d_rgbL)
+    pr = (C.c_void_p * n)(*d_rgbR)
+    ms = C.c_float()
+    L = lib()
+    L.ugsm_rowband_last_error.restype = C.c_char_p
+    rc = L.ugsm_rowband_match(hs, dv, n, pl, pr, rows, cols, C.c_size_t(step), split_levels, C.c_void_p(out[0]),
+                              C.c_void_p(out[1]), C.c_void_p(out[2]), C.byref(ms))
+    if rc != OK:
+        raise UgsmError(rc, L.ugsm_rowband_last_error().decode())
+    return ms.value
 
 
 def _p(a):
