@@ -220,6 +220,51 @@ def run_reference(args):
     return 0
 
 
+def rowband_block(n, L, R, steps, split_levels=3):
+    """One 16 MP pair over n GPUs in row bands (single process, C++ driver); ms per pair from CUDA events on rank 0's
+    stream, and a bit-for-bit comparison with the single-GPU result."""
+    import numpy as np
+    import torch
+
+    from ug_stereomatcher_b200 import capi
+
+    devs = list(range(n))
+    dL = [torch.from_numpy(L).to("cuda:%d" % d) for d in devs]
+    dR = [torch.from_numpy(R).to("cuda:%d" % d) for d in devs]
+    out = [torch.empty((ROWS, COLS), dtype=torch.float32, device="cuda:0") for _ in range(3)]
+    hs = [capi.Handle(device=d) for d in devs]
+    ms = [capi.rowband_match(hs, devs, [t.data_ptr() for t in dL], [t.data_ptr() for t in dR], ROWS, COLS, COLS * 3,
+                             [o.data_ptr() for o in out], split_levels) for _ in range(3 + steps)]
+    ref = [torch.empty((ROWS, COLS), dtype=torch.float32, device="cuda:0") for _ in range(3)]
+    with capi.Handle(device=0) as h1:
+        h1.match_full_device(dL[0].data_ptr(), dR[0].data_ptr(), ROWS, COLS, COLS * 3, *[t.data_ptr() for t in ref])
+        torch.cuda.synchronize(0)
+        same = all(bool(torch.equal(a, b)) for a, b in zip(out, ref))
+    for h in hs:
+        h.close()
+    return {"workload": "ONE 16MP pair, row-band partition over %d GPUs with NVLink halo exchange (BASELINE configs[2])" % n,
+            "ms_per_pair": float(np.median(ms[3:])), "n_gpus": n, "split_levels": split_levels,
+            "halo_rows": 16, "exchanges_per_pair": 12, "bit_exact_vs_single_gpu": same,
+            "driver": "ugsm_rowband_match (C++, one host thread per GPU, cudaMemcpy2DAsync peer copies, events)"}
+
+
+def run_rowband(args):
+    """--mode rowband: only section E of run_gpu, on all GPUs of the box (rank 0 drives them; other ranks exit)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    import numpy as np
+
+    synth = _synth()
+    L, R, _, _ = synth.make_pair(COLS, ROWS, 0)
+    lines = {"metric": "16MP_full_pyramid_HV_disparity_latency_rowband", "unit": "ms/pair", "higher_is_better": False,
+             "config": workload_config(), "data": "synthetic", "dtype": "f32", "scaling": "strong", "n_gpus": args.gpus}
+    blk = rowband_block(args.gpus, np.ascontiguousarray(L), np.ascontiguousarray(R), args.steps)
+    lines.update(value=blk["ms_per_pair"], ms_per_step=blk["ms_per_pair"], steps=args.steps, warmup=3, rowband=blk,
+                 vs_baseline=None)
+    emit_line(lines)
+    return 0
+
+
 def run_gpu(args):
     import threading
 
@@ -363,6 +408,19 @@ def run_gpu(args):
     fov_k1_ms = fovh.bench_correlate(fd.fov_width, fd.fov_height, 20)
     clocks = sampler.stop()
 
+    # ---- E. BASELINE configs[2]: ONE pair split into row bands over all N GPUs of the box (N > 1): rank 0's process
+    # drives every GPU through the C++ driver ugsm_rowband_match (one host thread per GPU, halo rows copied peer to
+    # peer over NVLink); the other ranks wait at the barrier with their GPUs idle ----
+    rowband = None
+    if world > 1:
+        # host-side (gloo) barriers: an NCCL barrier would leave a spinning kernel on the GPUs rank 0 is about to use
+        host_group = dist.new_group(backend="gloo")
+        barrier()
+        dist.barrier(group=host_group)
+        if rank == 0:
+            rowband = rowband_block(world, hostL[0].numpy(), hostR[0].numpy(), args.steps)
+        dist.barrier(group=host_group)
+
     # result sanity (not parity: tests/ do that): finite and close to the synthetic ground truth
     host_step(0, 0)
     _, _, dH, dV = make_pair_cached(rank * pool)
@@ -410,6 +468,8 @@ def run_gpu(args):
         }
         if cb:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if rowband:
+            line["rowband"] = rowband
         tpath = os.path.join(ROOT, "profiles", "traffic_k1.json")
         if os.path.exists(tpath):
             try:
@@ -466,8 +526,12 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "rowband"],
+                    help="pairs: pair-level data parallel throughput (default); rowband: one pair split over --gpus GPUs")
     a = ap.parse_args()
     if a.impl == "ours" and a.warmup < 3:
         a.warmup = 3  # timing rule: at least 3 warm-up steps
     claim_stdout()
-    sys.exit(run_reference(a) if a.impl == "reference" else run_gpu(a))
+    if a.impl == "reference":
+        sys.exit(run_reference(a))
+    sys.exit(run_rowband(a) if a.mode == "rowband" else run_gpu(a))
