@@ -279,6 +279,18 @@ int ugsm_cloud_from_match(ugsm_handle* h, const ugsm_camera_pair* cam, int src_l
 /* Device time of the last cloud kernel (CUDA events on the handle's stream). */
 int ugsm_cloud_last_ms(const ugsm_handle* h, float* ms);
 
+/* Range maps: what CdynamicCalibration::getRangePoint / getRangePointFOV (PC:951-1019) return at every pixel, i.e. the
+ * loops of doReconstruction_resized / doReconstructionFOV_resized (PC:730-751, 806-834) up to, not including, their
+ * cv::resize: z of the triangulated point (the two functions share get3DPoint's ZUp / divisor expressions), dense
+ * row-major rows x cols (fov_rows x fov_cols) floats as range_map.at<float>(jj, ii).  Bit-identical to that code. */
+int ugsm_range_full(ugsm_handle* h, const ugsm_camera_pair* cam, const float* H, const float* V, int rows, int cols,
+                    float* range);
+int ugsm_range_foveated(ugsm_handle* h, const ugsm_camera_pair* cam, const float* stackH, const float* stackV,
+                        int fov_rows, int fov_cols, int src_level, int im_rows, int im_cols, float* range);
+/* Same on the planes the last match left on the device (src_level < 0: full / composite; else that stack level);
+ * range: host buffer, or device buffer when range_on_device != 0. */
+int ugsm_range_from_match(ugsm_handle* h, const ugsm_camera_pair* cam, int src_level, float* range, int range_on_device);
+
 #ifdef __cplusplus
 }
 #endif

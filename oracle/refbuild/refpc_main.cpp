@@ -4,7 +4,9 @@
 // ugsmo_pointcloud_*) can be pinned against the real code.  CPU only.
 //
 //   refpc <in.bin> <out.bin>
-//   in : int32 mode(0 full, 1 foveated), rows, cols (of the disparity planes / of the fovea stack),
+//   in : int32 mode(0 full, 1 foveated; 2 / 3: the range maps of the same two inputs, i.e. getRangePoint /
+//        getRangePointFOV (getPointCloud.cpp:951-1019) at every pixel -- out: int64 n; n x float, row-major),
+//        rows, cols (of the disparity planes / of the fovea stack),
 //        im_rows, im_cols, sampling, src_level; double P1[12], P2[12]; float dX[rows*cols],
 //        dY[rows*cols]; uint8 bgr[im_rows*im_cols*3]
 //   out: int64 n; n x {float x, y, z; uint32 rgb}
@@ -67,6 +69,40 @@ int main(int argc, char** argv) {
     }
     node.P1_ = p1;
     node.P2_ = p2;
+    if (mode == 2 || mode == 3) {  // range maps: the loops of doReconstruction_resized / doReconstructionFOV_resized
+        std::vector<float> range;      // (getPointCloud.cpp:730-751, 806-834) up to, not including, cv::resize
+        int rr, rc;
+        if (mode == 2) {
+            node.foveated = 0;
+            node.dispX = dX;
+            node.dispY = dY;
+            rr = rows, rc = cols;
+            range.resize((size_t)rr * rc);
+            for (int ii = 0; ii < rc; ii++)
+                for (int jj = 0; jj < rr; jj++) range[(size_t)jj * rc + ii] = node.getRangePoint(ii, jj);
+        } else {
+            node.foveated = 1;
+            node.srcLevel = src_level;
+            node.destLevel = 0;
+            node.fdispX = dX;
+            node.fdispY = dY;
+            node.leftMargin_offset = node.left_marginOf_in(node.srcLevel, node.destLevel);
+            node.upperMargin_offset = node.upper_marginOf_in(node.srcLevel, node.destLevel);
+            node.fovH = node.fdispX.rows / foveaLevel;  // a macro of the reference source (getPointCloud.cpp:63)
+            node.fovW = node.fdispX.cols;
+            rr = node.fovH, rc = node.fovW;
+            range.resize((size_t)rr * rc);
+            for (int ii = 0; ii < rc; ii++)
+                for (int jj = 0; jj < rr; jj++) range[(size_t)jj * rc + ii] = node.getRangePointFOV(ii, jj);
+        }
+        FILE* o = fopen(argv[2], "wb");
+        if (!o) return 2;
+        int64_t n = (int64_t)range.size();
+        fwrite(&n, sizeof n, 1, o);
+        fwrite(range.data(), 4, range.size(), o);
+        fclose(o);
+        return 0;
+    }
     pcl::PointCloud<pcl::PointXYZRGB>::Ptr cloud;
     if (mode == 0) {
         node.foveated = 0;

@@ -138,4 +138,10 @@ int64_t ugsmo_cloud_foveated(const double P1[12], const double P2[12], const flo
 #ifdef __cplusplus
 }
 #endif
+/* Range maps (PC:951-1019): z of the triangulated point at every pixel, row-major. */
+int ugsmo_range_full(const double P1[12], const double P2[12], const float* dX, const float* dY, int rows, int cols,
+                     float* range);
+int ugsmo_range_foveated(const double P1[12], const double P2[12], const float* stackX, const float* stackY, int fov_h,
+                         int fov_w, int fovea_level, int src_level, int im_rows, int im_cols, float* range);
+
 #endif

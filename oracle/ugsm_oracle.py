@@ -378,9 +378,31 @@ def cloud_foveated(P1, P2, stackX, stackY, fov_h, src_level, im_rows, im_cols, i
     return pts
 
 
+def range_full(P1, P2, dX, dY):
+    """getRangePoint at every pixel (getPointCloud.cpp:951-982) -> (rows, cols) float32."""
+    dX, dY = _f(dX), _f(dY)
+    rows, cols = dX.shape
+    out = np.empty((rows, cols), np.float32)
+    if lib().ugsmo_range_full(_ptr(_cam(P1)), _ptr(_cam(P2)), _ptr(dX), _ptr(dY), rows, cols, _ptr(out)) != 0:
+        raise ValueError("ugsmo_range_full: invalid arguments")
+    return out
+
+
+def range_foveated(P1, P2, stackX, stackY, fov_h, src_level, im_rows, im_cols, fovea_level=7):
+    """getRangePointFOV at every fovea pixel of stack level src_level (getPointCloud.cpp:984-1019)."""
+    stackX, stackY = _f(stackX), _f(stackY)
+    fov_w = stackX.shape[1]
+    out = np.empty((fov_h, fov_w), np.float32)
+    if lib().ugsmo_range_foveated(_ptr(_cam(P1)), _ptr(_cam(P2)), _ptr(stackX), _ptr(stackY), fov_h, fov_w,
+                                  fovea_level, src_level, im_rows, im_cols, _ptr(out)) != 0:
+        raise ValueError("ugsmo_range_foveated: invalid arguments")
+    return out
+
+
 def run_refpc(mode, P1, P2, dX, dY, img, sampling=1, src_level=0, workdir=None):
     """Run oracle/_ref/refpc (the unmodified reference point-cloud source behind stubs).
-    mode 0: full cloud; mode 1: foveated cloud of stack level src_level.  -> (n, 4) float32."""
+    mode 0: full cloud; mode 1: foveated cloud of stack level src_level.  -> (n, 4) float32.
+    mode 2 / 3: the range maps of the same inputs (getRangePoint / getRangePointFOV) -> (n,) float32, row-major."""
     import struct
     import tempfile
 
@@ -401,4 +423,6 @@ def run_refpc(mode, P1, P2, dX, dY, img, sampling=1, src_level=0, workdir=None):
         subprocess.run([exe, fin, fout], check=True)
         raw = open(fout, "rb").read()
     n = struct.unpack("q", raw[:8])[0]
+    if mode >= 2:
+        return np.frombuffer(raw[8:], np.float32, n).copy()
     return np.frombuffer(raw[8:], np.float32).reshape(n, 4).copy()

@@ -194,3 +194,40 @@ int64_t ugsmo_cloud_foveated(const double P1[12], const double P2[12], const flo
     }
     return (int64_t)ncol * nrow;
 }
+
+/* Range maps: getRangePoint / getRangePointFOV (PC:951-1019) at every pixel, row-major as range_map.at<float>(jj, ii)
+ * (PC:749, 832).  Their ZUp and divisor expressions are the ones of get3DPoint, token for token (PC:937-944 vs
+ * PC:972-982), so the range is the z coordinate ugsmo_triangulate returns. */
+int ugsmo_range_full(const double P1[12], const double P2[12], const float* dX, const float* dY, int rows, int cols,
+                     float* range) {
+    if (rows <= 0 || cols <= 0) return -1;
+#pragma omp parallel for schedule(static)
+    for (int jj = 0; jj < rows; jj++)
+        for (int ii = 0; ii < cols; ii++) {
+            const size_t o = (size_t)jj * cols + ii;
+            float p[3];
+            ugsmo_triangulate(P1, P2, (float)ii, (float)jj, (float)ii + dX[o], (float)jj + dY[o], p);
+            range[o] = p[2];
+        }
+    return 0;
+}
+
+int ugsmo_range_foveated(const double P1[12], const double P2[12], const float* stackX, const float* stackY, int fov_h,
+                         int fov_w, int fovea_level, int src_level, int im_rows, int im_cols, float* range) {
+    if (fov_h <= 0 || fov_w <= 0 || src_level < 0 || src_level >= fovea_level) return -1;
+    int left, upper;
+    ugsmo_cloud_margins(im_rows, im_cols, fovea_level, src_level, &left, &upper);
+    const float sc = ugsmo_cloud_scale(src_level);
+#pragma omp parallel for schedule(static)
+    for (int jj = 0; jj < fov_h; jj++)
+        for (int ii = 0; ii < fov_w; ii++) {
+            const size_t o = (size_t)(jj + fov_h * src_level) * fov_w + ii;
+            const float x1 = (float)left + (float)ii * sc, y1 = (float)upper + (float)jj * sc; /* PC:988-992 */
+            const int sx = (int)((float)ii + stackX[o]), sy = (int)((float)jj + stackY[o]);       /* PC:994-995 */
+            const float x2 = (float)left + (float)sx * sc, y2 = (float)upper + (float)sy * sc;
+            float p[3];
+            ugsmo_triangulate(P1, P2, x1, y1, x2, y2, p);
+            range[(size_t)jj * fov_w + ii] = p[2];
+        }
+    return 0;
+}

@@ -70,6 +70,14 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "refpc_cloud.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
+    # range maps of the same inputs: getRangePoint / getRangePointFOV at every pixel (refpc modes 2 / 3)
+    rng_out = {}
+    for c in cloud_cases():
+        r = o.run_refpc(2 + c["mode"], c["P1"], c["P2"], c["dX"], c["dY"], c["img"], src_level=c["src_level"])
+        rng_out[c["name"]] = r.view(np.uint32)
+    path = os.path.join(ROOT, "tests", "golden", "refpc_range.npz")
+    np.savez_compressed(path, **rng_out)
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

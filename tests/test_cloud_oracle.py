@@ -67,6 +67,51 @@ def test_live_against_reference_binary(oracle, tmp_path):
     assert total > 10000
 
 
+def oracle_range(o, c):
+    if c["mode"] == 0:
+        return o.range_full(c["P1"], c["P2"], c["dX"], c["dY"])
+    return o.range_foveated(c["P1"], c["P2"], c["dX"], c["dY"], c["fov_h"], c["src_level"], c["img"].shape[0],
+                            c["img"].shape[1])
+
+
+def test_range_golden_matches_reference_outputs(oracle):
+    """Range maps (getRangePoint / getRangePointFOV, getPointCloud.cpp:951-1019): committed outputs of the unmodified
+    reference source (tests/golden/refpc_range.npz, refpc modes 2 / 3)."""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "refpc_range.npz"))
+    for c in cloud_cases():
+        got = oracle_range(oracle, c)
+        assert np.array_equal(got.view(np.uint32).ravel(), gold[c["name"]]), c["name"]
+        # and it is the z column of the cloud of the same inputs (the two functions share their Z expression)
+        if c["sampling"] == 1:
+            cloud = oracle_cloud(oracle, c)
+            z = cloud[:, 2].reshape(got.shape[1], got.shape[0]).T  # cloud order is column-major
+            assert np.array_equal(z.view(np.uint32), got.view(np.uint32)), c["name"]
+
+
+@pytest.mark.skipif(not os.path.exists(REFPC), reason="oracle/_ref/refpc not built (needs /root/reference)")
+def test_range_live_against_reference_binary(oracle, tmp_path):
+    rng = np.random.default_rng(78)
+    for t in range(4):
+        rows, cols = int(rng.integers(5, 80)), int(rng.integers(5, 110))
+        P1, P2 = cameras(rng, cols, rows)
+        dX = (rng.normal(0, 40, (rows, cols)) * (rng.random((rows, cols)) < 0.8)).astype(np.float32)
+        dY = np.round(rng.normal(0, 3, (rows, cols))).astype(np.float32)
+        img = np.zeros((rows, cols, 3), np.uint8)
+        ref = oracle.run_refpc(2, P1, P2, dX, dY, img, workdir=str(tmp_path)).reshape(rows, cols)
+        assert np.array_equal(ref.view(np.uint32), oracle.range_full(P1, P2, dX, dY).view(np.uint32))
+    for t in range(3):
+        im_rows, im_cols = int(rng.integers(300, 700)), int(rng.integers(400, 900))
+        fh, fw = fovea_dims(im_rows, im_cols)
+        P1, P2 = cameras(rng, im_cols, im_rows)
+        sX = rng.normal(0, 6, (7 * fh, fw)).astype(np.float32)
+        sY = rng.normal(0, 2, (7 * fh, fw)).astype(np.float32)
+        img = np.zeros((im_rows, im_cols, 3), np.uint8)
+        lev = int(rng.integers(0, 7))
+        ref = oracle.run_refpc(3, P1, P2, sX, sY, img, src_level=lev, workdir=str(tmp_path)).reshape(fh, fw)
+        mine = oracle.range_foveated(P1, P2, sX, sY, fh, lev, im_rows, im_cols)
+        assert np.array_equal(ref.view(np.uint32), mine.view(np.uint32))
+
+
 def test_rectified_pair_known_answer(oracle):
     """P1 = K[I|0], P2 = K[I|(-B,0,0)]: disparity d = x2 - x1 = -f*B/Z, so the closed form must return
     Z = -f*B/d, X = (x - cx) Z / f, Y = (y - cy) Z / f (to float accuracy; the formula is exact algebra)."""

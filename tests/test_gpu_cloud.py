@@ -210,3 +210,29 @@ def test_python_mirror_of_the_node_class(capi, gpu, oracle):
     same(node.doReconstructionRGB_FOV(f["dX"], f["dY"]),
          oracle.cloud_foveated(f["P1"], f["P2"], f["dX"], f["dY"], f["fov_h"], f["src_level"], f["img"].shape[0],
                                f["img"].shape[1], f["img"], sampling=f["sampling"]), "mirror foveated")
+
+
+def test_range_maps_vs_oracle_and_reference_golden(capi, gpu, oracle):
+    """Range maps (getRangePoint / getRangePointFOV): K5's range variant against the committed outputs of the unmodified
+    reference source and against the oracle, bit for bit; and from the planes a match left on the device."""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "refpc_range.npz"))
+    for c in cloud_cases():
+        cam = capi.CameraPair.of(c["P1"], c["P2"])
+        if c["mode"] == 0:
+            got = gpu.range_full(cam, c["dX"], c["dY"])
+        else:
+            got = gpu.range_foveated(cam, c["dX"], c["dY"], c["fov_h"], c["src_level"], c["img"].shape[0], c["img"].shape[1])
+        assert np.array_equal(bits(got).ravel(), gold[c["name"]]), c["name"]
+    rng = np.random.default_rng(5)
+    rows, cols = 257, 511
+    P1, P2 = cameras(rng, cols, rows)
+    dX = rng.normal(0, 9, (rows, cols)).astype(np.float32)
+    dY = rng.normal(0, 2, (rows, cols)).astype(np.float32)
+    same(gpu.range_full(capi.CameraPair.of(P1, P2), dX, dY), oracle.range_full(P1, P2, dX, dY), "range 257x511")
+    from ug_stereomatcher_b200 import synth
+    L, R, _, _ = synth.make_pair(320, 240, 3)
+    P1, P2 = cameras(rng, 320, 240)
+    with capi.Handle(levels=5) as h:
+        H, V, _ = h.match_full(L, R)
+        z = h.range_from_match(capi.CameraPair.of(P1, P2), 240, 320)
+    same(z, oracle.range_full(P1, P2, H, V), "range from the resident planes")

@@ -27,7 +27,7 @@ SYMBOLS = [
     "ugsm_band_level_info", "ugsm_band_iteration", "ugsm_band_upsample", "ugsm_band_emit", "ugsm_band_pack",
     "ugsm_band_unpack", "ugsm_cloud_count", "ugsm_cloud_full", "ugsm_cloud_full_device", "ugsm_cloud_foveated",
     "ugsm_cloud_from_match", "ugsm_cloud_last_ms", "ugsm_bench_pyramid", "ugsm_host_alloc", "ugsm_host_free",
-    "ugsm_rowband_match", "ugsm_rowband_last_error",
+    "ugsm_rowband_match", "ugsm_rowband_last_error", "ugsm_range_full", "ugsm_range_foveated", "ugsm_range_from_match",
 ]
 
 
@@ -344,6 +344,28 @@ class Handle:
                                            _p(pts), stride, C.byref(n)))
         assert n.value == pts.shape[0]
         return pts
+
+    def range_full(self, cam, H, V):
+        """getRangePoint at every pixel (getPointCloud.cpp:951-982) -> (rows, cols) float32."""
+        H, V = _f32(H), _f32(V)
+        rows, cols = H.shape
+        out = np.empty((rows, cols), np.float32)
+        self._ck(lib().ugsm_range_full(self._h, C.byref(cam), _p(H), _p(V), rows, cols, _p(out)))
+        return out
+
+    def range_foveated(self, cam, stackH, stackV, fov_rows, src_level, im_rows, im_cols):
+        """getRangePointFOV at every fovea pixel of stack level src_level (getPointCloud.cpp:984-1019)."""
+        stackH, stackV = _f32(stackH), _f32(stackV)
+        fov_cols = stackH.shape[1]
+        out = np.empty((fov_rows, fov_cols), np.float32)
+        self._ck(lib().ugsm_range_foveated(self._h, C.byref(cam), _p(stackH), _p(stackV), fov_rows, fov_cols, src_level,
+                                           im_rows, im_cols, _p(out)))
+        return out
+
+    def range_from_match(self, cam, rows, cols, src_level=-1):
+        out = np.empty((rows, cols), np.float32)
+        self._ck(lib().ugsm_range_from_match(self._h, C.byref(cam), src_level, _p(out), 0))
+        return out
 
     def cloud_from_match(self, cam, rows, cols, src_level=-1, sampling=1, stride=4, out=None, d_points=None):
         """Cloud of the pair last matched on this handle, from the device-resident planes.  rows, cols: extent of

@@ -937,11 +937,12 @@ int ensure_cloud_staging(ugsm_handle* h, size_t bytes) {
 // level of a fovea stack belonging to an im_rows x im_cols image.
 int launch_cloud(ugsm_handle* h, const ugsm_camera_pair* cam, const float* dX, const float* dY, int pitch, int rows,
                  int cols, int src_level, int im_rows, int im_cols, const uint8_t* d_img, size_t step, int bgr,
-                 int sampling, float* d_points, int stride, int64_t* npoints) {
-    if (!cam || !dX || !dY || !d_img || !d_points) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+                 int sampling, float* d_points, int stride, int64_t* npoints, float* d_range = nullptr) {
+    // d_range: the range map (z of every pixel, dense rows x cols) instead of a cloud; no image, no points
+    if (!cam || !dX || !dY || (!d_range && (!d_img || !d_points))) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
     if (rows < 1 || cols < 1 || sampling < 1) return fail(h, UGSM_ERR_INVALID, "bad rows/cols/sampling");
-    if (stride != 4 && stride != 8) return fail(h, UGSM_ERR_INVALID, "point stride must be 4 or 8 floats");
-    if ((reinterpret_cast<uintptr_t>(d_points) & 15) != 0)
+    if (!d_range && stride != 4 && stride != 8) return fail(h, UGSM_ERR_INVALID, "point stride must be 4 or 8 floats");
+    if (!d_range && (reinterpret_cast<uintptr_t>(d_points) & 15) != 0)
         return fail(h, UGSM_ERR_INVALID, "points not 16-byte aligned");
     K5Params p;
     memcpy(p.P1, cam->P1, sizeof p.P1);
@@ -950,6 +951,7 @@ int launch_cloud(ugsm_handle* h, const ugsm_camera_pair* cam, const float* dX, c
     p.img = d_img, p.step = step, p.bgr = bgr ? 1 : 0, p.sampling = sampling;
     p.ncol = div_up(cols, sampling), p.nrow = div_up(rows, sampling);
     p.points = d_points, p.stride = stride;
+    p.range = d_range;
     p.foveated = 0, p.left = p.upper = 0, p.scale = 1.0f;
     if (src_level >= 0) {
         if (src_level >= h->cfg.fovea_level)
@@ -1603,6 +1605,95 @@ int ugsm_cloud_last_ms(const ugsm_handle* h, float* ms) {
     if (!h || !ms) return UGSM_ERR_INVALID;
     *ms = h->cloud_ms;
     return UGSM_OK;
+}
+
+// ---- range maps (getRangePoint / getRangePointFOV, PC:951-1019): z of every pixel, dense row-major ----
+static int range_host(ugsm_handle* h, const ugsm_camera_pair* cam, const float* X, const float* Y, int rows, int cols,
+                      int src_level, int im_rows, int im_cols, float* range) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!cam || !X || !Y || !range) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+    if (rows < 1 || cols < 1 || im_rows < 1 || im_cols < 1) return fail(h, UGSM_ERR_INVALID, "bad rows/cols");
+    CK(cudaSetDevice(h->device));
+    const size_t plane_bytes = (size_t)rows * cols * sizeof(float), plane = (plane_bytes + 255) / 256 * 256;
+    int rc = ensure_cloud_staging(h, 3 * plane);
+    if (rc) return rc;
+    char* base = static_cast<char*>(h->cloud_buf);
+    float* dX = reinterpret_cast<float*>(base);
+    float* dY = reinterpret_cast<float*>(base + plane);
+    float* dZ = reinterpret_cast<float*>(base + 2 * plane);
+    const HostXfer xin[2] = {{X, dX, plane_bytes}, {Y, dY, plane_bytes}};
+    const HostXfer xout[1] = {{dZ, range, plane_bytes}};
+    const bool stage_in = want_staging(h, xin, 2, true), stage_out = want_staging(h, xout, 1, false);
+    if (stage_in || stage_out) {
+        rc = ensure_pinned(h, stage_in ? staged_bytes(xin, 2) : 0, stage_out ? staged_bytes(xout, 1) : 0);
+        if (rc) return rc;
+    }
+    if (stage_in) {
+        rc = staged_h2d(h, xin, 2);
+        if (rc) return rc;
+    } else {
+        for (int k = 0; k < 2; k++) CK(cudaMemcpyAsync(xin[k].dst, xin[k].src, xin[k].bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = launch_cloud(h, cam, dX, dY, cols, rows, cols, src_level, im_rows, im_cols, nullptr, 0, 0, 1, nullptr, 4,
+                      nullptr, dZ);
+    if (rc) return rc;
+    if (stage_out) {
+        rc = staged_d2h(h, xout, 1);
+        if (rc) return rc;
+    } else {
+        CK(cudaMemcpyAsync(range, dZ, plane_bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return finish_cloud(h);
+}
+
+int ugsm_range_full(ugsm_handle* h, const ugsm_camera_pair* cam, const float* H, const float* V, int rows, int cols,
+                    float* range) {
+    return range_host(h, cam, H, V, rows, cols, -1, rows, cols, range);
+}
+
+int ugsm_range_foveated(ugsm_handle* h, const ugsm_camera_pair* cam, const float* stackH, const float* stackV,
+                        int fov_rows, int fov_cols, int src_level, int im_rows, int im_cols, float* range) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!stackH || !stackV) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+    if (src_level < 0 || src_level >= h->cfg.fovea_level || fov_rows < 1 || fov_cols < 1)
+        return fail(h, UGSM_ERR_INVALID, "src_level %d outside the stack", src_level);
+    const size_t off = (size_t)src_level * fov_rows * fov_cols;  // PC:994: row yy + fovH * srcLevel
+    return range_host(h, cam, stackH + off, stackV + off, fov_rows, fov_cols, src_level, im_rows, im_cols, range);
+}
+
+int ugsm_range_from_match(ugsm_handle* h, const ugsm_camera_pair* cam, int src_level, float* range, int range_on_device) {
+    if (!h) return UGSM_ERR_INVALID;
+    if (!cam || !range) return fail(h, UGSM_ERR_INVALID, "null pointer argument");
+    if (h->last_kind < 0) return fail(h, UGSM_ERR_INVALID, "no match on this handle yet");
+    CK(cudaSetDevice(h->device));
+    const float *dX, *dY;
+    int pitch, rows, cols, lvl = -1;
+    if (src_level < 0) {
+        if (h->last_kind == 0) {
+            dX = h->lv[0].st[0], dY = h->lv[0].st[1], pitch = h->lv[0].mpitch;
+        } else if (h->last_kind == 2) {
+            dX = h->comp[0][0], dY = h->comp[0][1], pitch = h->lv[0].pitch;
+        } else {
+            return fail(h, UGSM_ERR_INVALID, "the last match was foveated: pass a stack level (or use ugsm_match_composite)");
+        }
+        rows = h->rows, cols = h->cols;
+    } else {
+        if (h->last_kind == 0) return fail(h, UGSM_ERR_INVALID, "the last match was not foveated");
+        if (src_level >= h->cfg.fovea_level) return fail(h, UGSM_ERR_INVALID, "src_level %d outside the stack", src_level);
+        const LevelBuf& b = h->lv[src_level];
+        dX = b.st[0], dY = b.st[1], pitch = b.mpitch, rows = b.mh, cols = b.mw, lvl = src_level;
+    }
+    const size_t bytes = (size_t)rows * cols * sizeof(float);
+    float* dZ = range;
+    if (!range_on_device) {
+        int rc = ensure_cloud_staging(h, bytes);
+        if (rc) return rc;
+        dZ = static_cast<float*>(h->cloud_buf);
+    }
+    int rc = launch_cloud(h, cam, dX, dY, pitch, rows, cols, lvl, h->rows, h->cols, nullptr, 0, 0, 1, nullptr, 4, nullptr, dZ);
+    if (rc) return rc;
+    if (!range_on_device) CK(cudaMemcpyAsync(range, dZ, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return finish_cloud(h);
 }
 
 int ugsm_get_pyramid_level(ugsm_handle* h, int level, float* left3, float* right3) {
