@@ -291,6 +291,48 @@ int ugsm_range_foveated(ugsm_handle* h, const ugsm_camera_pair* cam, const float
  * range: host buffer, or device buffer when range_on_device != 0. */
 int ugsm_range_from_match(ugsm_handle* h, const ugsm_camera_pair* cam, int src_level, float* range, int range_on_device);
 
+/* ---- Real-image feeder: image list -> TIFF decode -> ring of page-locked pair buffers.
+ * Replaces, for batch runs, the reference's camera simulator: Settings::readStringList / nextImage
+ * (include/ug_stereomatcher/settings.h:15-68: OpenCV FileStorage XML whose first top-level node is a sequence of
+ * paths, read two at a time as left, right; past the end the reader steps back to the next-to-last entry, i.e. it
+ * repeats the last pair) and RHcam_node::captureImage (src/utils/publish_images.cpp:128-211: cv::imread(path, 1),
+ * i.e. 8-bit, 3 channels, B,G,R byte order, handed on unswapped).  Decoded bytes are identical to cv::imread's for
+ * the supported TIFF variants (csrc/ugsm_feeder.cpp).  Relative paths are resolved against the list's directory.
+ * Host-only code. ---- */
+#define UGSM_FEEDER_END 100 /* ugsm_feeder_next: every pair has been handed out */
+typedef struct ugsm_feeder ugsm_feeder;
+typedef struct ugsm_feeder_pair {
+    const uint8_t* left;  /* rows x cols x 3 bytes (B,G,R), `step` bytes per row, page-locked when info.pinned */
+    const uint8_t* right;
+    int32_t rows, cols;
+    size_t step;
+    int64_t index; /* pair number, 0-based, in list order */
+    int32_t slot;  /* give back with ugsm_feeder_release once the match call that reads it has returned */
+} ugsm_feeder_pair;
+typedef struct ugsm_feeder_info_t {
+    int32_t rows, cols;
+    size_t step;
+    int64_t list_images; /* entries in the list */
+    int64_t pairs;       /* pairs this feeder delivers */
+    int32_t slots;
+    int32_t pinned;      /* 1: slots come from ugsm_host_alloc; 0: no CUDA device, ordinary memory */
+    double decode_ms;    /* decode time summed over the pairs decoded so far (all threads) */
+} ugsm_feeder_info_t;
+/* pairs <= 0: the list's own length / 2; pairs beyond the list repeat its last pair (settings.h:34-38).
+ * slots: pairs held in the ring; threads: decode threads running ahead of ugsm_feeder_next. */
+int ugsm_feeder_open(const char* list_xml, long pairs, int slots, int threads, ugsm_feeder** out);
+int ugsm_feeder_info(const ugsm_feeder* f, ugsm_feeder_info_t* out);
+/* Blocks until the next pair (list order) is decoded.  Thread-safe: concurrent callers get distinct pairs.
+ * UGSM_FEEDER_END after the last pair; a decode error is returned for that pair only. */
+int ugsm_feeder_next(ugsm_feeder* f, ugsm_feeder_pair* out);
+int ugsm_feeder_release(ugsm_feeder* f, int slot);
+int ugsm_feeder_close(ugsm_feeder* f);
+/* Error text of the feeder (f == NULL: of the calling thread's last failed open / tiff call). */
+const char* ugsm_feeder_last_error(const ugsm_feeder* f);
+/* One file: header fields, and the pixels as cv::imread(path, 1) returns them. */
+int ugsm_tiff_info(const char* path, int* rows, int* cols, int* samples, int* bits);
+int ugsm_tiff_read_bgr8(const char* path, uint8_t* dst, size_t step, int rows, int cols);
+
 #ifdef __cplusplus
 }
 #endif

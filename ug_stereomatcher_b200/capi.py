@@ -28,7 +28,10 @@ SYMBOLS = [
     "ugsm_band_unpack", "ugsm_cloud_count", "ugsm_cloud_full", "ugsm_cloud_full_device", "ugsm_cloud_foveated",
     "ugsm_cloud_from_match", "ugsm_cloud_last_ms", "ugsm_bench_pyramid", "ugsm_host_alloc", "ugsm_host_free",
     "ugsm_rowband_match", "ugsm_rowband_last_error", "ugsm_range_full", "ugsm_range_foveated", "ugsm_range_from_match",
+    "ugsm_feeder_open", "ugsm_feeder_info", "ugsm_feeder_next", "ugsm_feeder_release", "ugsm_feeder_close",
+    "ugsm_feeder_last_error", "ugsm_tiff_info", "ugsm_tiff_read_bgr8",
 ]
+FEEDER_END = 100
 
 
 class Config(C.Structure):
@@ -95,6 +98,16 @@ class CameraPair(C.Structure):
         c.P1[:] = [float(v) for v in np.asarray(P1, np.float64).reshape(12)]
         c.P2[:] = [float(v) for v in np.asarray(P2, np.float64).reshape(12)]
         return c
+
+
+class FeederPair(C.Structure):
+    _fields_ = [("left", C.c_void_p), ("right", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("step", C.c_size_t), ("index", C.c_int64), ("slot", C.c_int32)]
+
+
+class FeederInfo(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("step", C.c_size_t), ("list_images", C.c_int64),
+                ("pairs", C.c_int64), ("slots", C.c_int32), ("pinned", C.c_int32), ("decode_ms", C.c_double)]
 
 
 class UgsmError(RuntimeError):
@@ -164,6 +177,16 @@ def lib():
         L.ugsm_cloud_foveated.argtypes = [vp, cam, vp, vp, i, i, i, i, i, vp, sz, i, i, vp, i, i64p]
         L.ugsm_cloud_from_match.argtypes = [vp, cam, i, i, vp, i, i, i64p]
         L.ugsm_cloud_last_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        ip = C.POINTER(C.c_int)
+        L.ugsm_feeder_open.argtypes = [C.c_char_p, C.c_long, i, i, C.POINTER(vp)]
+        L.ugsm_feeder_info.argtypes = [vp, C.POINTER(FeederInfo)]
+        L.ugsm_feeder_next.argtypes = [vp, C.POINTER(FeederPair)]
+        L.ugsm_feeder_release.argtypes = [vp, i]
+        L.ugsm_feeder_close.argtypes = [vp]
+        L.ugsm_feeder_last_error.argtypes = [vp]
+        L.ugsm_feeder_last_error.restype = C.c_char_p
+        L.ugsm_tiff_info.argtypes = [C.c_char_p, ip, ip, ip, ip]
+        L.ugsm_tiff_read_bgr8.argtypes = [C.c_char_p, vp, sz, i, i]
         _LIB = L
     return _LIB
 
@@ -184,6 +207,66 @@ def query_dims(cfg, rows, cols, mode=0):
     if rc != OK:
         raise UgsmError(rc, "ugsm_query_dims: invalid rows/cols/mode/config")
     return d
+
+
+def tiff_read(path):
+    """ugsm_tiff_read_bgr8: the pixels of a TIFF file as cv::imread(path, 1) returns them (rows x cols x 3, B,G,R)."""
+    L = lib()
+    r, c, sp, b = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    rc = L.ugsm_tiff_info(os.fsencode(path), C.byref(r), C.byref(c), C.byref(sp), C.byref(b))
+    if rc != OK:
+        raise UgsmError(rc, L.ugsm_feeder_last_error(None).decode())
+    out = np.empty((r.value, c.value, 3), np.uint8)
+    rc = L.ugsm_tiff_read_bgr8(os.fsencode(path), out.ctypes.data, c.value * 3, r.value, c.value)
+    if rc != OK:
+        raise UgsmError(rc, L.ugsm_feeder_last_error(None).decode())
+    return out
+
+
+class Feeder:
+    """ugsm_feeder_*: image list -> TIFF decode threads -> ring of page-locked pair buffers (host-only)."""
+
+    def __init__(self, list_xml, pairs=0, slots=4, threads=2):
+        self._L = lib()
+        self._f = C.c_void_p()
+        rc = self._L.ugsm_feeder_open(os.fsencode(list_xml), pairs, slots, threads, C.byref(self._f))
+        if rc != OK:
+            self._f = None
+            raise UgsmError(rc, self._L.ugsm_feeder_last_error(None).decode())
+
+    def info(self):
+        fi = FeederInfo()
+        self._L.ugsm_feeder_info(self._f, C.byref(fi))
+        return fi
+
+    def next(self):
+        """Returns (FeederPair, left, right) with numpy views of the slot (valid until release), or None at the end."""
+        p = FeederPair()
+        rc = self._L.ugsm_feeder_next(self._f, C.byref(p))
+        if rc == FEEDER_END:
+            return None
+        if rc != OK:
+            raise UgsmError(rc, self._L.ugsm_feeder_last_error(self._f).decode())
+        n = p.rows * p.step
+        left = np.ctypeslib.as_array((C.c_uint8 * n).from_address(p.left)).reshape(p.rows, p.cols, 3)
+        right = np.ctypeslib.as_array((C.c_uint8 * n).from_address(p.right)).reshape(p.rows, p.cols, 3)
+        return p, left, right
+
+    def release(self, slot):
+        rc = self._L.ugsm_feeder_release(self._f, slot)
+        if rc != OK:
+            raise UgsmError(rc, "ugsm_feeder_release: slot %d is not handed out" % slot)
+
+    def close(self):
+        if self._f:
+            self._L.ugsm_feeder_close(self._f)
+            self._f = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def cloud_count(rows, cols, sampling=1):

@@ -5,9 +5,13 @@
 // independent.  Plain C-ABI only (include/ugsm.h), no CUDA toolchain needed to build this file.
 //
 //   ugsm_batch <rows> <cols> <pairs> [--devices 0,1,..] [--in-flight K] [--foveated] [--left l.rgb --right r.rgb]
+//              [--list images.xml [--decode-threads T] [--ring-slots S]]
 //
-// Without --left/--right a deterministic synthetic pair (hash noise, right = left shifted by 3 px) is used for
-// every index.  Prints one JSON line: pairs/s over the whole batch (wall clock, copies included), per-pair latency,
+// --list: real images.  The TIFF pairs of an OpenCV image list (the reference's src/utils/input_images.xml format)
+// are decoded by the library's feeder threads into a ring of page-locked buffers (ugsm_feeder_*, include/ugsm.h) and
+// matched straight from there; rows / cols are taken from the first image (pass 0 0), <pairs> beyond the list repeat
+// its last pair like the reference's reader.  Without --list and --left/--right a deterministic synthetic pair (hash
+// noise, right = left shifted by 3 px) is used for every index.  Prints one JSON line: pairs/s over the whole batch (wall clock, copies included), per-pair latency,
 // and a checksum of the last result (sum of H in double) that tests compare with the single-call path.
 #include <atomic>
 #include <chrono>
@@ -47,12 +51,13 @@ int main(int argc, char** argv) {
                 argv[0]);
         return 2;
     }
-    const int rows = atoi(argv[1]), cols = atoi(argv[2]);
+    int rows = atoi(argv[1]), cols = atoi(argv[2]);
     const long pairs = atol(argv[3]);
     std::vector<int> devices = {0};
     int in_flight = 4;
     bool fov = false;
-    const char *lf = nullptr, *rf = nullptr;
+    const char *lf = nullptr, *rf = nullptr, *list = nullptr;
+    int decode_threads = 4, ring_slots = 0;
     for (int i = 4; i < argc; i++) {
         if (!strcmp(argv[i], "--devices") && i + 1 < argc) {
             devices.clear();
@@ -65,7 +70,28 @@ int main(int argc, char** argv) {
             lf = argv[++i];
         } else if (!strcmp(argv[i], "--right") && i + 1 < argc) {
             rf = argv[++i];
+        } else if (!strcmp(argv[i], "--list") && i + 1 < argc) {
+            list = argv[++i];
+        } else if (!strcmp(argv[i], "--decode-threads") && i + 1 < argc) {
+            decode_threads = atoi(argv[++i]);
+        } else if (!strcmp(argv[i], "--ring-slots") && i + 1 < argc) {
+            ring_slots = atoi(argv[++i]);
         }
+    }
+    ugsm_feeder* feeder = nullptr;
+    if (list) {
+        if (in_flight < 1 || devices.empty() || pairs < 1) {
+            fprintf(stderr, "bad arguments\n");
+            return 2;
+        }
+        if (ring_slots < 1) ring_slots = (int)devices.size() * in_flight + 2;
+        if (ugsm_feeder_open(list, pairs, ring_slots, decode_threads, &feeder) != UGSM_OK) {
+            fprintf(stderr, "cannot open image list %s: %s\n", list, ugsm_feeder_last_error(nullptr));
+            return 2;
+        }
+        ugsm_feeder_info_t fi;
+        ugsm_feeder_info(feeder, &fi);
+        rows = fi.rows, cols = fi.cols;
     }
     if (rows < 1 || cols < 1 || pairs < 1 || in_flight < 1 || devices.empty()) {
         fprintf(stderr, "bad arguments\n");
@@ -128,11 +154,12 @@ int main(int argc, char** argv) {
         memcpy(k.L, L0.data(), img_bytes);
         memcpy(k.R, R0.data(), img_bytes);
     }
-    auto run_one = [&](Worker& k) -> int {
-        return fov ? ugsm_match_foveated(k.h, k.L, k.R, rows, cols, (size_t)cols * 3, k.out[0], k.out[1], k.out[2],
-                                         nullptr, nullptr)
-                   : ugsm_match_full(k.h, k.L, k.R, rows, cols, (size_t)cols * 3, k.out[0], k.out[1], k.out[2]);
+    auto run_pair = [&](Worker& k, const uint8_t* L, const uint8_t* R) -> int {
+        return fov ? ugsm_match_foveated(k.h, L, R, rows, cols, (size_t)cols * 3, k.out[0], k.out[1], k.out[2], nullptr,
+                                         nullptr)
+                   : ugsm_match_full(k.h, L, R, rows, cols, (size_t)cols * 3, k.out[0], k.out[1], k.out[2]);
     };
+    auto run_one = [&](Worker& k) -> int { return run_pair(k, k.L, k.R); };
     // warm-up: buffers, graphs and clocks, one pair per worker, concurrently
     {
         std::vector<std::thread> t;
@@ -154,10 +181,22 @@ int main(int argc, char** argv) {
         for (auto& k : w)
             t.emplace_back([&]() {
                 for (;;) {
-                    const long i = next.fetch_add(1);
-                    if (i >= pairs) break;
+                    ugsm_feeder_pair fp;
+                    if (feeder) {  // real images: the next decoded pair of the list, matched from its ring slot
+                        const int rc = ugsm_feeder_next(feeder, &fp);
+                        if (rc == UGSM_FEEDER_END) break;
+                        if (rc != UGSM_OK) {
+                            k.err = ugsm_feeder_last_error(feeder);
+                            break;
+                        }
+                    } else {
+                        const long i = next.fetch_add(1);
+                        if (i >= pairs) break;
+                    }
                     const auto a = std::chrono::steady_clock::now();
-                    if (run_one(k) != UGSM_OK) {
+                    const int mrc = feeder ? run_pair(k, fp.left, fp.right) : run_one(k);
+                    if (feeder) ugsm_feeder_release(feeder, fp.slot);
+                    if (mrc != UGSM_OK) {
                         k.err = ugsm_last_error(k.h);
                         break;
                     }
@@ -182,9 +221,18 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < out_floats; i++) h_sum += (double)w[0].out[0][i];
     printf("{\"tool\": \"ugsm_batch\", \"mode\": \"%s\", \"rows\": %d, \"cols\": %d, \"pairs\": %ld, \"gpus\": %zu, "
            "\"in_flight_per_gpu\": %d, \"wall_ms\": %.3f, \"pairs_per_s\": %.3f, \"ms_per_pair_latency\": %.3f, "
-           "\"h_sum\": %.9e}\n",
+           "\"h_sum\": %.9e",
            fov ? "foveated" : "full", rows, cols, done, devices.size(), in_flight, wall_ms, done / (wall_ms * 1e-3),
            done ? busy / done : 0.0, h_sum);
+    if (feeder) {
+        ugsm_feeder_info_t fi;
+        ugsm_feeder_info(feeder, &fi);
+        printf(", \"input\": \"tiff list\", \"list_images\": %lld, \"decode_threads\": %d, \"ring_slots\": %d, "
+               "\"ring_pinned\": %d, \"decode_ms_per_pair\": %.3f",
+               (long long)fi.list_images, decode_threads, fi.slots, fi.pinned, done ? fi.decode_ms / done : 0.0);
+        ugsm_feeder_close(feeder);
+    }
+    printf("}\n");
     for (auto& k : w) {
         ugsm_destroy(k.h);
         ugsm_host_free(k.L);
