@@ -17,7 +17,8 @@ path ("scaling": "weak"); torch.distributed (NCCL) is only the barrier and the m
             pair -- and, end to end, the PCIe copies -- behind the others).
             run.ms_per_pair_latency_device is the one-pair-in-flight latency.
   e2e       pairs/s through the host-buffer C-ABI call (ugsm_match_full) with pinned host
-            buffers: H2D of both images and D2H of H, V, C inside the timed region, same batch in flight
+            buffers: H2D of both images and D2H of H and V (the metric's planes; the confidence plane stays on
+            the device) inside the timed region, same batch in flight; e2e.with_confidence_plane = all three planes
   roofline  dominant kernel = K1 (fused warp+correlation+fit) at level 0, algorithmic bytes
             48 B/pixel (9 planes in, 3 out) / average launch time from CUDA
             events recorded around every level-0 K1 launch of an instrumented handle (use_graph = 2;
@@ -335,6 +336,13 @@ def run_gpu(args):
                                 *[t.data_ptr() for t in out[0]])
 
     def host_step(k, i):
+        # the metric's outputs, H and V, come back to the host; the confidence plane stays on the device (NULL output
+        # pointer) where its consumers (ugsm_cloud_from_match, the next pair's nothing) read it -- at 8 GPUs the host's
+        # aggregate DMA bandwidth, not the GPUs, bounds the end-to-end rate, so bytes that nobody reads are not copied
+        j = (i + k) % pool
+        handles[k].match_full(hostL[j].numpy(), hostR[j].numpy(), out=(hout[k][0].numpy(), hout[k][1].numpy(), None))
+
+    def host_step_hvc(k, i):
         j = (i + k) % pool
         handles[k].match_full(hostL[j].numpy(), hostR[j].numpy(), out=tuple(t.numpy() for t in hout[k]))
 
@@ -375,6 +383,7 @@ def run_gpu(args):
     ms_step, launches, _ = region(dev_step, NF, args.steps)
     # ---- B. end to end through the host-buffer C-ABI call (pinned host buffers), NF in flight ----
     e2e_ms_step, _, _ = region(host_step, NF, args.steps)
+    e2e_hvc_ms_step, _, _ = region(host_step_hvc, NF, max(3, args.steps // 2))  # all three planes to the host
     # ---- C. one pair in flight: latency per pair and the clean per-launch K1 timing (roofline) ----
     # (bracketed by cudaProfilerStart/Stop so that `ncu --profile-from-start off` instruments exactly this
     # region: one launch list per pair without slowing the other ~10k launches of the run down)
@@ -445,7 +454,11 @@ def run_gpu(args):
                     "sanity_epe_h_px": epe, "finite": finite,
                     "ms_per_pair_latency_device": lat_ms, "ms_per_pair_latency_e2e": e2e_lat_ms},
             "e2e": {"value": dp.throughput(NF, world, e2e_ms_step), "unit": UNIT, "ms_per_step": e2e_ms_step,
-                    "h2d_bytes_per_step": NF * 2 * ROWS * step_bytes, "d2h_bytes_per_step": NF * 3 * ROWS * COLS * 4},
+                    "h2d_bytes_per_step": NF * 2 * ROWS * step_bytes, "d2h_bytes_per_step": NF * 2 * ROWS * COLS * 4,
+                    "outputs_to_host": "H, V (the metric's planes); C stays in device memory (NULL output pointer)",
+                    "with_confidence_plane": {"value": dp.throughput(NF, world, e2e_hvc_ms_step), "unit": UNIT,
+                                              "ms_per_step": e2e_hvc_ms_step,
+                                              "d2h_bytes_per_step": NF * 3 * ROWS * COLS * 4}},
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},

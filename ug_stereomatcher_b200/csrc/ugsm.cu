@@ -99,11 +99,12 @@ struct ugsm_handle {
     void* tma_encode = nullptr;  // cuTensorMapEncodeTiled, fetched through cudaGetDriverEntryPoint
     int k2_stream = 1;        // large levels use the row pipeline k2_stream (UGSM_K2_STREAM=0: the tiled k2_smooth_box)
     int k2s_slots[K2S_MAX_PASSES + 1] = {};  // co-resident k2_stream CTAs on the device per pass count
-    int k2s_min_seg = 48;     // shortest row segment of a strip (UGSM_K2S_MIN_SEG)
-    long k2s_min_pixels = 1500000;  // k2_stream runs levels of at least this many pixels (UGSM_K2S_MIN_PIXELS) ...
-    int k2s_max_passes = 6;         // ... and at most this many smoothing passes (UGSM_K2S_MAX_PASSES)
+    int k2s_min_seg = 24;     // shortest row segment of a strip (UGSM_K2S_MIN_SEG)
+    long k2s_min_pixels = 400000;   // k2_stream runs levels of at least this many pixels (UGSM_K2S_MIN_PIXELS) ...
+    int k2s_max_passes = 10;        // ... and at most this many smoothing passes (UGSM_K2S_MAX_PASSES)
+    int k2s_edge_extra = 2;         // extra row segments of the edge strips, whose steps are slower (UGSM_K2S_EDGE_EXTRA)
     long k1_small_pixels = 400000;  // levels below this use k1_correlate_small (UGSM_K1_SMALL_PIXELS)
-    long k2_small_pixels = 700000;  // levels below this use k2_smooth_box_small (UGSM_K2_SMALL_PIXELS)
+    long k2_small_pixels = 400000;  // levels below this use k2_smooth_box_small (UGSM_K2_SMALL_PIXELS)
     int k0_rows_dense = 16, k0_rows_dec = 8;  // output rows per warp of k0_march5 (UGSM_K0_ROWS_DENSE / _DEC)
     // CUDA graph of the per-pair launch sequence (pyramid levels .. last level), valid for the current shape
     cudaGraphExec_t graph_exec = nullptr;
@@ -278,13 +279,24 @@ int set_kernel_attrs(ugsm_handle* h) {
     if (const char* e = getenv("UGSM_K2_STREAM")) h->k2_stream = atoi(e);
     if (const char* e = getenv("UGSM_K2S_MIN_SEG")) h->k2s_min_seg = atoi(e) > 0 ? atoi(e) : h->k2s_min_seg;
     if (const char* e = getenv("UGSM_K2S_MIN_PIXELS")) h->k2s_min_pixels = atol(e);
+    if (const char* e = getenv("UGSM_K2S_EDGE_EXTRA")) h->k2s_edge_extra = std::max(0, atoi(e));
     if (const char* e = getenv("UGSM_K2S_MAX_PASSES")) h->k2s_max_passes = std::min(K2S_MAX_PASSES, std::max(0, atoi(e)));
-    CK(cudaFuncSetAttribute(k2_stream, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CK(cudaFuncSetAttribute(k2_stream<K2S_NT_SMALL, K2S_MINB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)k2s_smem_bytes(K2S_NT_SMALL / 32 - 2)));
+    CK(cudaFuncSetAttribute(k2_stream<K2S_NT_SMALL, K2S_MINB_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k2_stream<K2S_NT_LARGE, K2S_MINB_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)k2s_smem_bytes(K2S_MAX_PASSES)));
-    CK(cudaFuncSetAttribute(k2_stream, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k2_stream<K2S_NT_LARGE, K2S_MINB_LARGE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
     for (int sps = 0; sps <= K2S_MAX_PASSES; sps++) {
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k2_stream, (sps + 2) * 32, k2s_smem_bytes(sps)));
+        if ((sps + 2) * 32 <= K2S_NT_SMALL)
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k2_stream<K2S_NT_SMALL, K2S_MINB_SMALL>, (sps + 2) * 32,
+                                                             k2s_smem_bytes(sps)));
+        else
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k2_stream<K2S_NT_LARGE, K2S_MINB_LARGE>, (sps + 2) * 32,
+                                                             k2s_smem_bytes(sps)));
         h->k2s_slots[sps] = std::max(1, nb) * h->sm_count;
     }
     if (const char* e = getenv("UGSM_K2S_SLOTS"))
@@ -383,11 +395,16 @@ void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci
         sp.k.th = 0;
         const int strips = div_up(w, K2_BW - 2 * p.hpad);
         const int brows = y_end - y_begin;
-        int nseg = std::max(1, h->k2s_slots[passes] / strips);
+        // one co-resident wave: interior strips x nseg segments plus the (at most 3) edge strips' extra segment
+        int nseg = std::max(1, (h->k2s_slots[passes] - 3 * h->k2s_edge_extra) / strips);
         nseg = std::min(nseg, std::max(1, brows / h->k2s_min_seg));
-        sp.seg_rows = div_up(brows, nseg);
-        dim3 grid(strips, div_up(brows, sp.seg_rows));
-        k2_stream<<<grid, (passes + 2) * 32, k2s_smem_bytes(passes), h->stream>>>(sp);
+        sp.nseg = nseg;
+        sp.edge_extra = h->k2s_edge_extra;
+        dim3 grid(strips, nseg + sp.edge_extra);
+        if ((passes + 2) * 32 <= K2S_NT_SMALL)
+            k2_stream<K2S_NT_SMALL, K2S_MINB_SMALL><<<grid, (passes + 2) * 32, k2s_smem_bytes(passes), h->stream>>>(sp);
+        else
+            k2_stream<K2S_NT_LARGE, K2S_MINB_LARGE><<<grid, (passes + 2) * 32, k2s_smem_bytes(passes), h->stream>>>(sp);
         h->launches++;
         return;
     }
