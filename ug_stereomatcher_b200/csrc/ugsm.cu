@@ -102,6 +102,7 @@ struct ugsm_handle {
     int k2s_min_seg = 24;     // shortest row segment of a strip (UGSM_K2S_MIN_SEG)
     long k2s_min_pixels = 400000;   // k2_stream runs levels of at least this many pixels (UGSM_K2S_MIN_PIXELS) ...
     int k2s_max_passes = 10;        // ... and at most this many smoothing passes (UGSM_K2S_MAX_PASSES)
+    int pdl = 1;                    // programmatic dependent launch of the coarse-level kernels (UGSM_PDL)
     int k2s_edge_extra = 2;         // extra row segments of the edge strips, whose steps are slower (UGSM_K2S_EDGE_EXTRA)
     long k1_small_pixels = 400000;  // levels below this use k1_correlate_small (UGSM_K1_SMALL_PIXELS)
     long k2_small_pixels = 400000;  // levels below this use k2_smooth_box_small (UGSM_K2_SMALL_PIXELS)
@@ -280,6 +281,7 @@ int set_kernel_attrs(ugsm_handle* h) {
     if (const char* e = getenv("UGSM_K2S_MIN_SEG")) h->k2s_min_seg = atoi(e) > 0 ? atoi(e) : h->k2s_min_seg;
     if (const char* e = getenv("UGSM_K2S_MIN_PIXELS")) h->k2s_min_pixels = atol(e);
     if (const char* e = getenv("UGSM_K2S_EDGE_EXTRA")) h->k2s_edge_extra = std::max(0, atoi(e));
+    if (const char* e = getenv("UGSM_PDL")) h->pdl = atoi(e);
     if (const char* e = getenv("UGSM_K2S_MAX_PASSES")) h->k2s_max_passes = std::min(K2S_MAX_PASSES, std::max(0, atoi(e)));
     CK(cudaFuncSetAttribute(k2_stream<K2S_NT_SMALL, K2S_MINB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)k2s_smem_bytes(K2S_NT_SMALL / 32 - 2)));
@@ -322,6 +324,28 @@ bool make_plane_map(ugsm_handle* h, CUtensorMap* tm, const float* plane, int w, 
                                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Launch of a launch-bound kernel as a programmatic dependent of its predecessor in the stream (pdl_wait /
+// pdl_trigger in ugsm_kernels.cuh); UGSM_PDL=0 restores ordinary launches.  No dynamic shared memory.
+template <typename... KArgs, typename... Args>
+void launch_pdl(ugsm_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    // Inside a graph capture the attribute would become a programmatic edge; measured, graph replay is faster with
+    // ordinary kernel-to-kernel edges (16 MP pair 13.8 vs 14.2 ms), so only plain stream launches use it
+    // (use_graph = 0: 15.0 -> 14.6 ms).
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (h->pdl) cudaStreamIsCapturing(h->stream, &cs);
+    cfg.numAttrs = (h->pdl && cs == cudaStreamCaptureStatusNone) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 void launch_k1(ugsm_handle* h, const K1Params& p, const int* fast_flag = nullptr) {
     // Large levels: streaming strip march (k1_stream): one warp per 30-column strip and row segment; the
     // segment length is chosen so that all CTAs of the launch are co-resident (one wave, no tail).
@@ -352,7 +376,7 @@ void launch_k1(ugsm_handle* h, const K1Params& p, const int* fast_flag = nullptr
         k1_correlate<4, K1_TH><<<grid, 128, sizeof(K1Smem<4, K1_TH>), h->stream>>>(p);
     } else {
         dim3 grid(div_up(p.w, 30), div_up(p.h, K1S_TH));
-        k1_correlate_small<K1S_TH><<<grid, 256, 0, h->stream>>>(p);
+        launch_pdl(h, k1_correlate_small<K1S_TH>, grid, dim3(256), p);
     }
     h->launches++;
 }
@@ -382,7 +406,7 @@ void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci
         p.hpad = R;
         const int side = K2S_T + 2 * R;
         dim3 grid(div_up(w, K2S_T), div_up(hh, K2S_T));
-        k2_smooth_box_small<<<grid, align_up(side * side, 32), 0, h->stream>>>(p);
+        launch_pdl(h, k2_smooth_box_small, grid, dim3(align_up(side * side, 32)), p);
         h->launches++;
         return;
     }
@@ -426,8 +450,8 @@ void launch_k3(ugsm_handle* h, float* const src[3], int w, int hh, int spitch, i
                float* const dst[3], int ow, int oh, int dpitch, int oy_begin = 0, int oy_end = -1) {
     if (oy_end < 0) oy_end = oh;
     dim3 block(32, 8), grid(div_up(ow, 32), div_up(oy_end - oy_begin, 8));
-    k3_upsample<<<grid, block, 0, h->stream>>>(src[0], src[1], src[2], w, hh, spitch, crop_x, crop_y, dst[0], dst[1],
-                                               dst[2], ow, oy_end, dpitch, oy_begin);
+    launch_pdl(h, k3_upsample, grid, block, (const float*)src[0], (const float*)src[1], (const float*)src[2], w, hh, spitch,
+               crop_x, crop_y, dst[0], dst[1], dst[2], ow, oy_end, dpitch, oy_begin);
     h->launches++;
 }
 
@@ -1756,550 +1780,9 @@ int ugsm_get_level_disparity(ugsm_handle* h, int level, float* H, float* V, floa
     return UGSM_OK;
 }
 
-// ------------------------------------------------------------------- stage entry points
-int ugsm_stage_pyramid(ugsm_handle* h, const uint8_t* rgb, int rows, int cols, size_t step, float* const* out3) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (!rgb || !out3 || step < (size_t)cols * 3) return fail(h, UGSM_ERR_INVALID, "bad argument");
-    CK(cudaSetDevice(h->device));
-    int rc = prepare_shape(h, rows, cols, 0);
-    if (rc) return rc;
-    const size_t rgb_bytes = step * (size_t)(rows - 1) + (size_t)cols * 3;  // the last row ends after cols*3 bytes
-    rc = ensure_staging(h, rgb_bytes, 1);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(h->d_rgb[0], rgb, rgb_bytes, cudaMemcpyHostToDevice, h->stream));
-    unpack_images(h, h->d_rgb[0], nullptr, step);
-    build_pyramid(h, 1);
-    CK(cudaGetLastError());
-    for (int l = 0; l < h->cfg.levels; l++) {
-        if (!out3[l]) continue;
-        LevelBuf& b = h->lv[l];
-        size_t n = (size_t)b.w * b.h;
-        for (int k = 0; k < 3; k++) CK(down2d(out3[l] + k * n, b.L[k], b.pitch, b.w, b.h, h->stream));
-    }
-    CK(cudaStreamSynchronize(h->stream));
-    return UGSM_OK;
-}
-
-int ugsm_stage_correlate(ugsm_handle* h, const float* L3, const float* R3, const float* H, const float* V,
-                         const float* C, int width, int height, float threshold, int first_coarsest, float* Hn,
-                         float* Vn, float* Cn, int32_t* dbg_srcx, int32_t* dbg_srcy, uint8_t* dbg_branch_h,
-                         uint8_t* dbg_branch_v) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (!L3 || !R3 || !H || !V || !C || !Hn || !Vn || !Cn || width < 1 || height < 1)
-        return fail(h, UGSM_ERR_INVALID, "bad argument");
-    CK(cudaSetDevice(h->device));
-    int rc = set_kernel_attrs(h);
-    if (rc) return rc;
-    TmpDev td;
-    int pitch = align_up(width, 32);
-    size_t n = (size_t)width * height, np = (size_t)pitch * height;
-    float* d[15];
-    for (auto& p : d)
-        if (!(p = td.alloc<float>(np))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
-    bool dbg = dbg_srcx && dbg_srcy && dbg_branch_h && dbg_branch_v;
-    int32_t *dsx = nullptr, *dsy = nullptr;
-    uint8_t *dbh = nullptr, *dbv = nullptr;
-    if (dbg) {
-        dsx = td.alloc<int32_t>(n);
-        dsy = td.alloc<int32_t>(n);
-        dbh = td.alloc<uint8_t>(n);
-        dbv = td.alloc<uint8_t>(n);
-        if (!dsx || !dsy || !dbh || !dbv) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
-    }
-    for (int k = 0; k < 3; k++) {
-        CK(up2d(d[k], pitch, L3 + k * n, width, height, h->stream));
-        CK(up2d(d[3 + k], pitch, R3 + k * n, width, height, h->stream));
-    }
-    CK(up2d(d[9], pitch, H, width, height, h->stream));
-    CK(up2d(d[10], pitch, V, width, height, h->stream));
-    CK(up2d(d[11], pitch, C, width, height, h->stream));
-    K1Params p;
-    launch_energy(h, d, d + 6, 3, width, height, pitch);
-    for (int k = 0; k < 3; k++) {
-        p.L[k] = d[k];
-        p.R[k] = d[3 + k];
-        p.U[k] = d[6 + k];
-    }
-    p.H = d[9];
-    p.V = d[10];
-    p.C = d[11];
-    p.Hn = d[12];
-    p.Vn = d[13];
-    p.Cn = d[14];
-    p.w = width;
-    p.h = height;
-    p.pitch = pitch;
-    p.y_begin = 0;
-    p.y_end = height;
-    p.T = threshold;
-    p.first_coarsest = first_coarsest ? 1 : 0;
-    p.dbg_srcx = dsx;
-    p.dbg_srcy = dsy;
-    p.dbg_bh = dbh;
-    p.dbg_bv = dbv;
-    p.tp = h->taps;
-    launch_range_flag(h, d, d + 3, width, height, pitch, h->d_flags + UGSM_MAX_LEVELS);
-    launch_k1(h, p, h->d_flags + UGSM_MAX_LEVELS);
-    CK(cudaGetLastError());
-    CK(down2d(Hn, d[12], pitch, width, height, h->stream));
-    CK(down2d(Vn, d[13], pitch, width, height, h->stream));
-    CK(down2d(Cn, d[14], pitch, width, height, h->stream));
-    if (dbg) {
-        CK(cudaMemcpyAsync(dbg_srcx, dsx, n * 4, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(dbg_srcy, dsy, n * 4, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(dbg_branch_h, dbh, n, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(dbg_branch_v, dbv, n, cudaMemcpyDeviceToHost, h->stream));
-    }
-    CK(cudaStreamSynchronize(h->stream));
-    return UGSM_OK;
-}
-
-int ugsm_stage_smooth(ugsm_handle* h, float* H, float* V, float* C, int width, int height, int passes) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (!H || !V || !C || width < 1 || height < 1 || passes < 0 || passes > 16)
-        return fail(h, UGSM_ERR_INVALID, "bad argument");
-    CK(cudaSetDevice(h->device));
-    int rc = set_kernel_attrs(h);
-    if (rc) return rc;
-    TmpDev td;
-    int pitch = align_up(width, 32);
-    size_t np = (size_t)pitch * height;
-    float* d[6];
-    for (auto& p : d)
-        if (!(p = td.alloc<float>(np))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
-    float* io[3] = {H, V, C};
-    for (int k = 0; k < 3; k++) CK(up2d(d[k], pitch, io[k], width, height, h->stream));
-    launch_k2(h, d[0], d[1], d[2], d[3], d[4], d[5], width, height, pitch, passes);
-    CK(cudaGetLastError());
-    for (int k = 0; k < 3; k++) CK(down2d(io[k], d[3 + k], pitch, width, height, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return UGSM_OK;
-}
-
-int ugsm_stage_upsample(ugsm_handle* h, const float* H, const float* V, const float* C, int width, int height,
-                        int fine_w, int fine_h, int crop_x, int crop_y, int out_w, int out_h, float* Ho, float* Vo,
-                        float* Co) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (!H || !V || !C || !Ho || !Vo || !Co || width < 1 || height < 1 || out_w < 1 || out_h < 1 || crop_x < 0 ||
-        crop_y < 0 || crop_x + out_w > fine_w || crop_y + out_h > fine_h)
-        return fail(h, UGSM_ERR_INVALID, "bad argument");
-    CK(cudaSetDevice(h->device));
-    TmpDev td;
-    int sp = align_up(width, 32), dp = align_up(out_w, 32);
-    float *s[3], *d[3];
-    for (auto& p : s)
-        if (!(p = td.alloc<float>((size_t)sp * height))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
-    for (auto& p : d)
-        if (!(p = td.alloc<float>((size_t)dp * out_h))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
-    const float* in[3] = {H, V, C};
-    float* out[3] = {Ho, Vo, Co};
-    for (int k = 0; k < 3; k++) CK(up2d(s[k], sp, in[k], width, height, h->stream));
-    launch_k3(h, s, width, height, sp, crop_x, crop_y, d, out_w, out_h, dp);
-    CK(cudaGetLastError());
-    for (int k = 0; k < 3; k++) CK(down2d(out[k], d[k], dp, out_w, out_h, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return UGSM_OK;
-}
-
-int ugsm_stage_match_level(ugsm_handle* h, const float* L3, const float* R3, float* H, float* V, float* C, int width,
-                           int height, int iters, int passes, int coarsest) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (!L3 || !R3 || !H || !V || !C || width < 1 || height < 1 || iters < 0 || passes < 0 || passes > 16)
-        return fail(h, UGSM_ERR_INVALID, "bad argument");
-    CK(cudaSetDevice(h->device));
-    int rc = set_kernel_attrs(h);
-    if (rc) return rc;
-    TmpDev td;
-    int pitch = align_up(width, 32);
-    size_t n = (size_t)width * height, np = (size_t)pitch * height;
-    float* d[15];
-    for (auto& p : d)
-        if (!(p = td.alloc<float>(np))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
-    float* io[3] = {H, V, C};
-    for (int k = 0; k < 3; k++) {
-        CK(up2d(d[k], pitch, L3 + k * n, width, height, h->stream));
-        CK(up2d(d[3 + k], pitch, R3 + k * n, width, height, h->stream));
-        CK(up2d(d[9 + k], pitch, io[k], width, height, h->stream));
-    }
-    launch_energy(h, d, d + 6, 3, width, height, pitch);
-    launch_range_flag(h, d, d + 3, width, height, pitch, h->d_flags + UGSM_MAX_LEVELS);
-    run_level(h, d, d + 3, d + 6, d + 9, d + 12, width, height, pitch, iters, passes, coarsest != 0, -1,
-              h->d_flags + UGSM_MAX_LEVELS);
-    CK(cudaGetLastError());
-    for (int k = 0; k < 3; k++) CK(down2d(io[k], d[9 + k], pitch, width, height, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return UGSM_OK;
-}
-
-// ------------------------------------------------------------------- row-band execution
-int ugsm_band_begin(ugsm_handle* h, const uint8_t* d_rgbL, const uint8_t* d_rgbR, int rows, int cols, size_t step,
-                    int split_levels) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (!d_rgbL || !d_rgbR || step < (size_t)cols * 3) return fail(h, UGSM_ERR_INVALID, "bad argument");
-    const int levels = h->cfg.levels;
-    if (split_levels < 1 || split_levels >= levels) return fail(h, UGSM_ERR_INVALID, "split_levels out of range");
-    CK(cudaSetDevice(h->device));
-    int rc = set_kernel_attrs(h);
-    if (rc) return rc;
-    rc = prepare_shape(h, rows, cols, 0);
-    if (rc) return rc;
-    h->launches = 0;
-    h->kev_used = 0;
-    unpack_images(h, d_rgbL, d_rgbR, step);
-    auto replicated = [&]() -> int {
-        build_pyramid(h, 2);
-        prepare_levels(h);
-        int r = run_levels(h, levels - 1, split_levels, false);
-        if (r) return r;
-        LevelBuf& c = h->lv[split_levels];
-        LevelBuf& b = h->lv[split_levels - 1];
-        launch_k3(h, c.st, c.mw, c.mh, c.mpitch, 0, 0, b.st, b.mw, b.mh, b.mpitch);
-        return UGSM_OK;
-    };
-    if (!h->cfg.use_graph) {
-        rc = replicated();
-        if (rc) return rc;
-    } else {
-        if (h->band_graph && h->band_graph_split != split_levels) {
-            cudaGraphExecDestroy(h->band_graph);
-            h->band_graph = nullptr;
-        }
-        if (!h->band_graph) {
-            const int l0 = h->launches;
-            cudaGraph_t g = nullptr;
-            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
-            rc = replicated();
-            cudaError_t e = cudaStreamEndCapture(h->stream, &g);
-            if (rc || e != cudaSuccess || !g) {
-                if (g) cudaGraphDestroy(g);
-                return rc ? rc : fail(h, UGSM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-            }
-            e = cudaGraphInstantiate(&h->band_graph, g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) {
-                h->band_graph = nullptr;
-                return fail(h, UGSM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-            }
-            h->band_graph_split = split_levels;
-            h->band_graph_launches = h->launches - l0;
-            h->launches = l0;
-        }
-        CK(cudaGraphLaunch(h->band_graph, h->stream));
-        h->launches += h->band_graph_launches;
-    }
-    CK(cudaGetLastError());
-    return UGSM_OK;
-}
-
-int ugsm_band_level_info(ugsm_handle* h, int level, ugsm_band_level* out) {
-    if (!h || !out) return UGSM_ERR_INVALID;
-    if (h->lv.empty() || level < 0 || level >= (int)h->lv.size()) return fail(h, UGSM_ERR_INVALID, "no such level");
-    LevelBuf& b = h->lv[level];
-    out->width = b.mw;
-    out->height = b.mh;
-    out->pitch = b.mpitch;
-    out->iters = b.iters;
-    out->smooth = b.smooth;
-    for (int k = 0; k < 3; k++) out->state[k] = b.st[k];
-    return UGSM_OK;
-}
-
-int ugsm_band_iteration(ugsm_handle* h, int level, int m, int y_begin, int y_end, int ext) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (h->lv.empty() || level < 0 || level >= (int)h->lv.size()) return fail(h, UGSM_ERR_INVALID, "no such level");
-    LevelBuf& b = h->lv[level];
-    if (m < 1 || m > b.iters || y_begin < 0 || y_end > b.mh || y_begin >= y_end || ext < b.smooth + 1)
-        return fail(h, UGSM_ERR_INVALID, "bad band iteration arguments");
-    CK(cudaSetDevice(h->device));
-    float T = 1.0f;  // MGL:1673, replayed up to iteration m
-    for (int k = 1; k < m; k++) T = threshold_after(b.iters, k, T);
-    K1Params p;
-    for (int k = 0; k < 3; k++) {
-        p.L[k] = b.Lm[k];
-        p.R[k] = b.Rm[k];
-        p.U[k] = b.U[k];
-    }
-    p.H = b.st[0];
-    p.V = b.st[1];
-    p.C = b.st[2];
-    p.Hn = h->tmp[0];
-    p.Vn = h->tmp[1];
-    p.Cn = h->tmp[2];
-    p.w = b.mw;
-    p.h = b.mh;
-    p.pitch = b.mpitch;
-    p.y_begin = y_begin - ext < 0 ? 0 : y_begin - ext;
-    p.y_end = y_end + ext > b.mh ? b.mh : y_end + ext;
-    p.T = T;
-    p.first_coarsest = (level == h->cfg.levels - 1 && m == 1) ? 1 : 0;
-    p.dbg_srcx = p.dbg_srcy = nullptr;
-    p.dbg_bh = p.dbg_bv = nullptr;
-    p.tp = h->taps;
-    launch_k1(h, p, h->d_flags + level);
-    launch_k2(h, h->tmp[0], h->tmp[1], h->tmp[2], b.st[0], b.st[1], b.st[2], b.mw, b.mh, b.mpitch, b.smooth, y_begin,
-              y_end);
-    CK(cudaGetLastError());
-    return UGSM_OK;
-}
-
-int ugsm_band_upsample(ugsm_handle* h, int level, int y_begin, int y_end) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (h->lv.empty() || level < 1 || level >= (int)h->lv.size()) return fail(h, UGSM_ERR_INVALID, "no such level");
-    LevelBuf& c = h->lv[level];
-    LevelBuf& b = h->lv[level - 1];
-    if (y_begin < 0) y_begin = 0;
-    if (y_end > b.mh) y_end = b.mh;
-    if (y_begin >= y_end) return fail(h, UGSM_ERR_INVALID, "empty row range");
-    CK(cudaSetDevice(h->device));
-    launch_k3(h, c.st, c.mw, c.mh, c.mpitch, 0, 0, b.st, b.mw, b.mh, b.mpitch, y_begin, y_end);
-    CK(cudaGetLastError());
-    return UGSM_OK;
-}
-
-static int band_copy(ugsm_handle* h, int level, int y_begin, int y_end, float* buf, bool pack) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (h->lv.empty() || level < 0 || level >= (int)h->lv.size() || !buf)
-        return fail(h, UGSM_ERR_INVALID, "bad argument");
-    LevelBuf& b = h->lv[level];
-    if (y_begin < 0 || y_end > b.mh || y_begin >= y_end) return fail(h, UGSM_ERR_INVALID, "bad row range");
-    CK(cudaSetDevice(h->device));
-    const size_t n = (size_t)(y_end - y_begin) * b.mpitch;
-    for (int k = 0; k < 3; k++) {
-        float* plane = b.st[k] + (size_t)y_begin * b.mpitch;
-        if (pack)
-            CK(cudaMemcpyAsync(buf + k * n, plane, n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-        else
-            CK(cudaMemcpyAsync(plane, buf + k * n, n * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-    }
-    return UGSM_OK;
-}
-int ugsm_band_pack(ugsm_handle* h, int level, int y_begin, int y_end, float* d_buf) {
-    return band_copy(h, level, y_begin, y_end, d_buf, true);
-}
-int ugsm_band_unpack(ugsm_handle* h, int level, int y_begin, int y_end, const float* d_buf) {
-    return band_copy(h, level, y_begin, y_end, const_cast<float*>(d_buf), false);
-}
-
-int ugsm_band_emit(ugsm_handle* h, float* dH, float* dV, float* dC, int y_begin, int y_end) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (h->lv.empty() || !dH || !dV || !dC) return fail(h, UGSM_ERR_INVALID, "bad argument");
-    LevelBuf& b = h->lv[0];
-    if (y_begin < 0 || y_end > b.mh || y_begin >= y_end) return fail(h, UGSM_ERR_INVALID, "bad row range");
-    CK(cudaSetDevice(h->device));
-    const size_t so = (size_t)y_begin * b.mpitch, dd = (size_t)y_begin * b.mw;
-    launch_copy3(h, b.st[0] + so, b.st[1] + so, b.st[2] + so, b.mpitch, dH + dd, dV + dd, dC + dd, b.mw, b.mw,
-                 y_end - y_begin);
-    CK(cudaGetLastError());
-    return UGSM_OK;
-}
-
-// ------------------------------------------------------------------- micro-benchmarks
-__global__ void k_fill_synth(float* p, size_t n, float lo, float hi, uint32_t seed) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t x = (uint32_t)i * 2654435761u + seed;
-    x ^= x >> 16;
-    x *= 0x7feb352du;
-    x ^= x >> 15;
-    x *= 0x846ca68bu;
-    x ^= x >> 16;
-    p[i] = lo + (hi - lo) * (float)(x >> 8) * (1.0f / 16777216.0f);
-}
-
-int ugsm_bench_correlate(ugsm_handle* h, int width, int height, int reps, float* avg_ms) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (width < 1 || height < 1 || reps < 1 || !avg_ms) return fail(h, UGSM_ERR_INVALID, "bad argument");
-    CK(cudaSetDevice(h->device));
-    int rc = set_kernel_attrs(h);
-    if (rc) return rc;
-    TmpDev td;
-    int pitch = align_up(width, 32);
-    size_t np = (size_t)pitch * height;
-    float* d[15];
-    for (auto& p : d)
-        if (!(p = td.alloc<float>(np))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
-    int blocks = (int)((np + 255) / 256);
-    for (int k = 0; k < 6; k++) k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[k], np, 16.f, 240.f, 17u * k + 1);
-    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[9], np, -2.f, 2.f, 101u);
-    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[10], np, -1.f, 1.f, 102u);
-    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[11], np, 0.3f, 1.f, 103u);
-    K1Params p;
-    launch_energy(h, d, d + 6, 3, width, height, pitch);
-    for (int k = 0; k < 3; k++) {
-        p.L[k] = d[k];
-        p.R[k] = d[3 + k];
-        p.U[k] = d[6 + k];
-    }
-    p.H = d[9];
-    p.V = d[10];
-    p.C = d[11];
-    p.Hn = d[12];
-    p.Vn = d[13];
-    p.Cn = d[14];
-    p.w = width;
-    p.h = height;
-    p.pitch = pitch;
-    p.y_begin = 0;
-    p.y_end = height;
-    p.T = 1.0f;
-    p.first_coarsest = 0;
-    p.dbg_srcx = p.dbg_srcy = nullptr;
-    p.dbg_bh = p.dbg_bv = nullptr;
-    p.tp = h->taps;
-    launch_range_flag(h, d, d + 3, width, height, pitch, h->d_flags + UGSM_MAX_LEVELS);
-    const int* ff = h->d_flags + UGSM_MAX_LEVELS;
-    for (int i = 0; i < 3; i++) launch_k1(h, p, ff);
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, h->stream));
-    for (int i = 0; i < reps; i++) launch_k1(h, p, ff);
-    CK(cudaEventRecord(e1, h->stream));
-    CK(cudaEventSynchronize(e1));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    CK(cudaGetLastError());
-    *avg_ms = ms / reps;
-    return UGSM_OK;
-}
-
-__global__ void k_poly_test(const float* l, const float* c, const float* r, float T, float* off, float* conf,
-                            uint8_t* br, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float o, cf;
-    int b;
-    poly_fit(l[i], c[i], r[i], T, o, cf, b);
-    off[i] = o;
-    conf[i] = cf;
-    br[i] = (uint8_t)b;
-}
-
-/* PolyDisparity (ML:790-843) on n (l, c, r) triples: the device function K1 uses, for exhaustive parity tests. */
-int ugsm_stage_poly(ugsm_handle* h, const float* l, const float* c, const float* r, int n, float T, float* offset,
-                    float* conf, uint8_t* branch) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (!l || !c || !r || !offset || !conf || !branch || n < 1) return fail(h, UGSM_ERR_INVALID, "bad argument");
-    CK(cudaSetDevice(h->device));
-    TmpDev td;
-    float* d[5];
-    for (auto& p : d)
-        if (!(p = td.alloc<float>(n))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
-    uint8_t* db = td.alloc<uint8_t>(n);
-    if (!db) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
-    CK(cudaMemcpyAsync(d[0], l, n * 4, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(d[1], c, n * 4, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(d[2], r, n * 4, cudaMemcpyHostToDevice, h->stream));
-    k_poly_test<<<div_up(n, 256), 256, 0, h->stream>>>(d[0], d[1], d[2], T, d[3], d[4], db, n);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(offset, d[3], n * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(conf, d[4], n * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(branch, db, n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return UGSM_OK;
-}
-
-__global__ void k_null(int) {}
-
-/* K0 timing: kind 0 = left-energy (dense, 3 planes), 1 = blur + odd-sample decimation (6 planes), 2 = blur +
- * sqrt2 decimation (6 planes) of width x height planes; average of `reps` launches. */
-int ugsm_bench_pyramid(ugsm_handle* h, int width, int height, int kind, int reps, float* avg_ms) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (width < 8 || height < 8 || reps < 1 || kind < 0 || kind > 2 || !avg_ms)
-        return fail(h, UGSM_ERR_INVALID, "bad argument");
-    CK(cudaSetDevice(h->device));
-    int rc = set_kernel_attrs(h);
-    if (rc) return rc;
-    const int n = kind == 0 ? 3 : 6;
-    const int w2 = kind == 0 ? width : (kind == 1 ? (int)((int)(width / SCALE_D) / SCALE_D) : (int)(width / SCALE_D));
-    const int h2 = kind == 0 ? height : (kind == 1 ? (int)((int)(height / SCALE_D) / SCALE_D) : (int)(height / SCALE_D));
-    const int sp = align_up(width, 32), dp = align_up(w2, 32);
-    TmpDev tmp;
-    const float* src[6];
-    float* dst[6];
-    for (int k = 0; k < n; k++) {
-        float* s = tmp.alloc<float>((size_t)sp * height);
-        dst[k] = tmp.alloc<float>((size_t)dp * h2);
-        if (!s || !dst[k]) return fail(h, UGSM_ERR_NOMEM, "bench allocation failed");
-        k_fill_synth<<<div_up(sp * height, 256), 256, 0, h->stream>>>(s, (size_t)sp * height, 16.f, 240.f, 17u * k + 1);
-        src[k] = s;
-    }
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    for (int i = 0; i < reps + 2; i++) {
-        if (i == 2) CK(cudaEventRecord(e0, h->stream));
-        if (kind == 0)
-            launch_energy(h, src, dst, n, width, height, sp);
-        else
-            launch_blur_decimate(h, kind == 2 ? 0 : 1, src, dst, n, width, height, sp, w2, h2, dp);
-    }
-    CK(cudaEventRecord(e1, h->stream));
-    CK(cudaEventSynchronize(e1));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    CK(cudaGetLastError());
-    *avg_ms = ms / reps;
-    return UGSM_OK;
-}
-
-/* Launch floor: average time of `reps` back-to-back empty launches on the handle's stream. */
-int ugsm_bench_null(ugsm_handle* h, int reps, float* avg_ms) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (reps < 1 || !avg_ms) return fail(h, UGSM_ERR_INVALID, "bad argument");
-    CK(cudaSetDevice(h->device));
-    for (int i = 0; i < 10; i++) k_null<<<1, 32, 0, h->stream>>>(i);
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, h->stream));
-    for (int i = 0; i < reps; i++) k_null<<<1, 32, 0, h->stream>>>(i);
-    CK(cudaEventRecord(e1, h->stream));
-    CK(cudaEventSynchronize(e1));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    *avg_ms = ms / reps;
-    return UGSM_OK;
-}
-
-int ugsm_bench_smooth(ugsm_handle* h, int width, int height, int passes, int reps, float* avg_ms) {
-    if (!h) return UGSM_ERR_INVALID;
-    if (width < 1 || height < 1 || reps < 1 || passes < 0 || passes > 16 || !avg_ms)
-        return fail(h, UGSM_ERR_INVALID, "bad argument");
-    CK(cudaSetDevice(h->device));
-    int rc = set_kernel_attrs(h);
-    if (rc) return rc;
-    TmpDev td;
-    int pitch = align_up(width, 32);
-    size_t np = (size_t)pitch * height;
-    float* d[6];
-    for (auto& p : d)
-        if (!(p = td.alloc<float>(np))) return fail(h, UGSM_ERR_NOMEM, "cudaMalloc failed");
-    int blocks = (int)((np + 255) / 256);
-    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[0], np, -2.f, 2.f, 101u);
-    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[1], np, -1.f, 1.f, 102u);
-    k_fill_synth<<<blocks, 256, 0, h->stream>>>(d[2], np, 0.3f, 1.f, 103u);
-    for (int i = 0; i < 3; i++) launch_k2(h, d[0], d[1], d[2], d[3], d[4], d[5], width, height, pitch, passes);
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, h->stream));
-    for (int i = 0; i < reps; i++) launch_k2(h, d[0], d[1], d[2], d[3], d[4], d[5], width, height, pitch, passes);
-    CK(cudaEventRecord(e1, h->stream));
-    CK(cudaEventSynchronize(e1));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    CK(cudaGetLastError());
-    *avg_ms = ms / reps;
-    return UGSM_OK;
-}
+#include "ugsm_band_api.inc"
+#ifndef UGSM_NO_TEST_API
+#include "ugsm_test_api.inc"
+#endif
 
 }  // extern "C"
