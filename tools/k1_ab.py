@@ -6,6 +6,8 @@ from ug_stereomatcher_b200 import capi
 SIZES = [(4928, 3264), (3484, 2307), (2463, 1631), (1741, 1153), (1231, 815), (870, 576), (615, 407), (434, 287)]
 VARIANTS = [("tiled", dict(UGSM_K1_STREAM=0)), ("stream generic", dict(UGSM_K1_STREAM=1, UGSM_K1_FAST=0)),
             ("stream fast", dict(UGSM_K1_STREAM=1, UGSM_K1_FAST=1))]
+if os.environ.get("K1_SIZES"):  # e.g. K1_SIZES=615x407,434x287
+    SIZES = [tuple(int(v) for v in t.split("x")) for t in os.environ["K1_SIZES"].split(",")]
 extra = dict(kv.split("=") for kv in sys.argv[1:])
 for name, env in VARIANTS:
     os.environ.update({k: str(v) for k, v in env.items()})

@@ -92,7 +92,7 @@ struct ugsm_handle {
     int k1_nw = 2;
     int k1_stream = 1;        // large levels use the streaming strip march k1_stream (UGSM_K1_STREAM=0: the tiled k1_correlate)
     int k1s_slots = 0;        // co-resident k1_stream CTAs on the device (occupancy x SM count)
-    int k1s_min_seg = 32;     // shortest row segment of a strip (UGSM_K1S_MIN_SEG)
+    int k1s_min_seg = 8;      // shortest row segment of a strip (UGSM_K1S_MIN_SEG)
     int* d_flags = nullptr;   // per level: nonzero when the six matcher planes lie in [1, 256] (k1_stream FAST march)
     int k1_fast = 1;          // UGSM_K1_FAST=0: always take the guarded GENERIC march
     int k1_tma = 1;           // left image / U / C rows of k1_stream arrive as TMA tiles (UGSM_K1_TMA=0: cp.async)
@@ -104,7 +104,7 @@ struct ugsm_handle {
     int k2s_max_passes = 10;        // ... and at most this many smoothing passes (UGSM_K2S_MAX_PASSES)
     int pdl = 1;                    // programmatic dependent launch of the coarse-level kernels (UGSM_PDL)
     int k2s_edge_extra = 2;         // extra row segments of the edge strips, whose steps are slower (UGSM_K2S_EDGE_EXTRA)
-    long k1_small_pixels = 400000;  // levels below this use k1_correlate_small (UGSM_K1_SMALL_PIXELS)
+    long k1_small_pixels = 200000;  // levels below this use k1_correlate_small (UGSM_K1_SMALL_PIXELS)
     long k2_small_pixels = 400000;  // levels below this use k2_smooth_box_small (UGSM_K2_SMALL_PIXELS)
     int k0_rows_dense = 16, k0_rows_dec = 8;  // output rows per warp of k0_march5 (UGSM_K0_ROWS_DENSE / _DEC)
     // CUDA graph of the per-pair launch sequence (pyramid levels .. last level), valid for the current shape
