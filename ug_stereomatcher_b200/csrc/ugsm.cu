@@ -104,6 +104,7 @@ struct ugsm_handle {
     int k2s_max_passes = 10;        // ... and at most this many smoothing passes (UGSM_K2S_MAX_PASSES)
     int pdl = 1;                    // programmatic dependent launch of the coarse-level kernels (UGSM_PDL)
     int k2s_edge_extra = 2;         // extra row segments of the edge strips, whose steps are slower (UGSM_K2S_EDGE_EXTRA)
+    long k1_tiny_pixels = 20000;    // levels below this use 2-row k1_correlate_small tiles (UGSM_K1_TINY_PIXELS)
     long k1_small_pixels = 200000;  // levels below this use k1_correlate_small (UGSM_K1_SMALL_PIXELS)
     long k2_small_pixels = 400000;  // levels below this use k2_smooth_box_small (UGSM_K2_SMALL_PIXELS)
     int k0_rows_dense = 16, k0_rows_dec = 8;  // output rows per warp of k0_march5 (UGSM_K0_ROWS_DENSE / _DEC)
@@ -237,7 +238,8 @@ int compute_dims(const ugsm_config& c, int rows, int cols, int mode, ugsm_dims* 
 
 // ------------------------------------------------------------------ kernel launchers
 constexpr int K1_TH = 16;
-constexpr int K1S_TH = 8;
+constexpr int K1S_TH = 4;       // rows of a k1_correlate_small tile (two half-strips of 2 rows: 6 march steps)
+constexpr int K1S_TH_TINY = 2;  // ... on the tiniest levels (5 march steps, twice the CTAs)
 // K0: the register-marching kernels win on large planes (HBM-bound), the tiled one on small planes (latency-bound)
 constexpr long K0_MARCH_DENSE_PIXELS = 900000;  // output pixels
 constexpr long K0_MARCH_DEC_PIXELS = 200000;
@@ -272,6 +274,7 @@ int set_kernel_attrs(ugsm_handle* h) {
         if (const char* e = getenv("UGSM_K1S_SLOTS")) h->k1s_slots = atoi(e) > 0 ? atoi(e) : h->k1s_slots;
     }
     if (const char* e = getenv("UGSM_K1_SMALL_PIXELS")) h->k1_small_pixels = atol(e);
+    if (const char* e = getenv("UGSM_K1_TINY_PIXELS")) h->k1_tiny_pixels = atol(e);
     if (const char* e = getenv("UGSM_K2_SMALL_PIXELS")) h->k2_small_pixels = atol(e);
     if (const char* e = getenv("UGSM_K0_ROWS_DENSE")) h->k0_rows_dense = atoi(e) > 0 ? atoi(e) : h->k0_rows_dense;
     if (const char* e = getenv("UGSM_K0_ROWS_DEC")) h->k0_rows_dec = atoi(e) > 0 ? atoi(e) : h->k0_rows_dec;
@@ -375,8 +378,15 @@ void launch_k1(ugsm_handle* h, const K1Params& p, const int* fast_flag = nullptr
         dim3 grid(div_up(p.w, 120), div_up(band_rows, K1_TH));
         k1_correlate<4, K1_TH><<<grid, 128, sizeof(K1Smem<4, K1_TH>), h->stream>>>(p);
     } else {
-        dim3 grid(div_up(p.w, 30), div_up(p.h, K1S_TH));
-        launch_pdl(h, k1_correlate_small<K1S_TH>, grid, dim3(256), p);
+        // latency-bound: the march pays a 4-step prologue per tile, so short tiles on more SMs are faster
+        // (8 -> 4 rows: 16 MP pair 13.33 -> 13.16 ms, 640x480 3.33 -> 2.85 ms; 2 rows only pay on the tiniest levels)
+        if ((long)p.w * p.h < h->k1_tiny_pixels) {
+            dim3 grid(div_up(p.w, 30), div_up(p.h, K1S_TH_TINY));
+            launch_pdl(h, k1_correlate_small<K1S_TH_TINY>, grid, dim3(256), p);
+        } else {
+            dim3 grid(div_up(p.w, 30), div_up(p.h, K1S_TH));
+            launch_pdl(h, k1_correlate_small<K1S_TH>, grid, dim3(256), p);
+        }
     }
     h->launches++;
 }
