@@ -25,7 +25,7 @@ for k in range(4):
         names.append("%s%d.tif" % (tag, k))
 with open(os.path.join(d, "list.xml"), "w") as f:
     f.write('<?xml version="1.0"?>\n<opencv_storage>\n<images>\n%s\n</images>\n</opencv_storage>\n' % "\n".join(names))
-for threads in (8, 24):
+for threads in (8, 16, 24):
     p = subprocess.run([batch, "0", "0", str(pairs), "--devices", devs, "--in-flight", "4", "--list",
                         os.path.join(d, "list.xml"), "--decode-threads", str(threads)], stdout=subprocess.PIPE)
     print(p.stdout.decode().strip(), flush=True)

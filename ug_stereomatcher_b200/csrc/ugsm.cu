@@ -104,6 +104,8 @@ struct ugsm_handle {
     int k2s_max_passes = 10;        // ... and at most this many smoothing passes (UGSM_K2S_MAX_PASSES)
     int pdl = 1;                    // programmatic dependent launch of the coarse-level kernels (UGSM_PDL)
     int k2s_edge_extra = 2;         // extra row segments of the edge strips, whose steps are slower (UGSM_K2S_EDGE_EXTRA)
+    long k2_tiny_pixels = 0;        // levels below this use k2_tiny_tile-sided k2_smooth_box_small tiles (UGSM_K2_TINY_PIXELS)
+    int k2_tiny_tile = 8;           // (UGSM_K2_TINY_TILE)
     long k1_tiny_pixels = 20000;    // levels below this use 2-row k1_correlate_small tiles (UGSM_K1_TINY_PIXELS)
     long k1_small_pixels = 200000;  // levels below this use k1_correlate_small (UGSM_K1_SMALL_PIXELS)
     long k2_small_pixels = 400000;  // levels below this use k2_smooth_box_small (UGSM_K2_SMALL_PIXELS)
@@ -275,6 +277,8 @@ int set_kernel_attrs(ugsm_handle* h) {
     }
     if (const char* e = getenv("UGSM_K1_SMALL_PIXELS")) h->k1_small_pixels = atol(e);
     if (const char* e = getenv("UGSM_K1_TINY_PIXELS")) h->k1_tiny_pixels = atol(e);
+    if (const char* e = getenv("UGSM_K2_TINY_PIXELS")) h->k2_tiny_pixels = atol(e);
+    if (const char* e = getenv("UGSM_K2_TINY_TILE")) h->k2_tiny_tile = std::min(K2S_T, std::max(2, atoi(e)));
     if (const char* e = getenv("UGSM_K2_SMALL_PIXELS")) h->k2_small_pixels = atol(e);
     if (const char* e = getenv("UGSM_K0_ROWS_DENSE")) h->k0_rows_dense = atoi(e) > 0 ? atoi(e) : h->k0_rows_dense;
     if (const char* e = getenv("UGSM_K0_ROWS_DEC")) h->k0_rows_dec = atoi(e) > 0 ? atoi(e) : h->k0_rows_dec;
@@ -412,10 +416,13 @@ void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci
     const int R = passes + 1;
     if (!banded && (long)w * hh < h->k2_small_pixels && K2S_T + 2 * R <= 32) {
         // small levels: 16x16 tiles, one thread per region cell (latency-oriented)
-        p.th = K2S_T;
+        // latency-bound like K1-small: on the tiniest levels smaller tiles (fewer warps at the per-pass barrier, more
+        // SMs busy) are faster although the halo is recomputed more often
+        const int tt = ((long)w * hh < h->k2_tiny_pixels) ? h->k2_tiny_tile : K2S_T;
+        p.th = tt;
         p.hpad = R;
-        const int side = K2S_T + 2 * R;
-        dim3 grid(div_up(w, K2S_T), div_up(hh, K2S_T));
+        const int side = tt + 2 * R;
+        dim3 grid(div_up(w, tt), div_up(hh, tt));
         launch_pdl(h, k2_smooth_box_small, grid, dim3(align_up(side * side, 32)), p);
         h->launches++;
         return;

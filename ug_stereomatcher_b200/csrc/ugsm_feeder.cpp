@@ -569,8 +569,13 @@ void decode_loop(ugsm_feeder* f) {
         }
         struct timespec a, b;
         clock_gettime(CLOCK_MONOTONIC, &a);
-        int rc = load_image(f->path_of(2 * i), s->L, f->step, f->rows, f->cols);
-        if (rc == UGSM_OK) rc = load_image(f->path_of(2 * i + 1), s->R, f->step, f->rows, f->cols);
+        int rc;
+        try {  // nothing may escape a decode thread
+            rc = load_image(f->path_of(2 * i), s->L, f->step, f->rows, f->cols);
+            if (rc == UGSM_OK) rc = load_image(f->path_of(2 * i + 1), s->R, f->step, f->rows, f->cols);
+        } catch (...) {
+            rc = ffail(UGSM_ERR_NOMEM, "out of memory while decoding pair %s%ld", "", i);
+        }
         clock_gettime(CLOCK_MONOTONIC, &b);
         {
             std::lock_guard<std::mutex> lk(f->mu);
@@ -642,40 +647,34 @@ int ugsm_feeder_open(const char* list_xml, long pairs, int slots, int threads, u
         f->step = (size_t)f->cols * 3;
         const size_t bytes = f->step * f->rows;
         f->slots.resize((size_t)slots);
+        // page-locked slots; without a CUDA device the ring still works with ordinary memory (ugsm_match_* stages
+        // pageable buffers itself)
         f->pinned = true;
         for (auto& s : f->slots) {
             void *l = nullptr, *r = nullptr;
-            if (f->pinned && (ugsm_host_alloc(bytes, &l) != UGSM_OK || ugsm_host_alloc(bytes, &r) != UGSM_OK)) {
-                // no CUDA device: the ring still works with ordinary memory (ugsm_match_* stages pageable buffers itself)
+            if (ugsm_host_alloc(bytes, &l) != UGSM_OK || ugsm_host_alloc(bytes, &r) != UGSM_OK) {
                 if (l) ugsm_host_free(l);
-                l = r = nullptr;
                 f->pinned = false;
-                for (auto& q : f->slots) {
-                    if (q.L) ugsm_host_free(q.L), ugsm_host_free(q.R);
-                    q.L = q.R = nullptr;
-                }
+                break;
             }
-            if (!f->pinned) {
-                l = aligned_alloc(4096, (bytes + 4095) / 4096 * 4096);
-                r = aligned_alloc(4096, (bytes + 4095) / 4096 * 4096);
-                if (!l || !r) {
-                    free(l), free(r);
+            s.L = (uint8_t*)l, s.R = (uint8_t*)r;
+        }
+        if (!f->pinned) {
+            for (auto& s : f->slots) {
+                if (s.L) ugsm_host_free(s.L);
+                if (s.R) ugsm_host_free(s.R);
+                s.L = s.R = nullptr;
+            }
+            const size_t padded = (bytes + 4095) / 4096 * 4096;
+            for (auto& s : f->slots) {
+                s.L = (uint8_t*)aligned_alloc(4096, padded);
+                s.R = (uint8_t*)aligned_alloc(4096, padded);
+                if (!s.L || !s.R) {
                     ugsm_feeder_close(f);
                     return ffail(UGSM_ERR_NOMEM, "ugsm_feeder_open: out of host memory");
                 }
             }
-            s.L = (uint8_t*)l, s.R = (uint8_t*)r;
         }
-        if (!f->pinned)
-            for (auto& s : f->slots)  // slots allocated before the switch to ordinary memory were freed above
-                if (!s.L) {
-                    s.L = (uint8_t*)aligned_alloc(4096, (bytes + 4095) / 4096 * 4096);
-                    s.R = (uint8_t*)aligned_alloc(4096, (bytes + 4095) / 4096 * 4096);
-                    if (!s.L || !s.R) {
-                        ugsm_feeder_close(f);
-                        return ffail(UGSM_ERR_NOMEM, "ugsm_feeder_open: out of host memory");
-                    }
-                }
         for (int i = 0; i < threads; i++) f->threads.emplace_back(decode_loop, f);
         *out = f;
         return UGSM_OK;
