@@ -104,7 +104,7 @@ struct ugsm_handle {
     int k2s_max_passes = 10;        // ... and at most this many smoothing passes (UGSM_K2S_MAX_PASSES)
     int pdl = 1;                    // programmatic dependent launch of the coarse-level kernels (UGSM_PDL)
     int k2s_edge_extra = 2;         // extra row segments of the edge strips, whose steps are slower (UGSM_K2S_EDGE_EXTRA)
-    long k2_tiny_pixels = 0;        // levels below this use k2_tiny_tile-sided k2_smooth_box_small tiles (UGSM_K2_TINY_PIXELS)
+    long k2_tiny_pixels = 20000;     // levels below this use k2_tiny_tile-sided k2_smooth_box_small tiles (UGSM_K2_TINY_PIXELS)
     int k2_tiny_tile = 8;           // (UGSM_K2_TINY_TILE)
     long k1_tiny_pixels = 20000;    // levels below this use 2-row k1_correlate_small tiles (UGSM_K1_TINY_PIXELS)
     long k1_small_pixels = 200000;  // levels below this use k1_correlate_small (UGSM_K1_SMALL_PIXELS)
