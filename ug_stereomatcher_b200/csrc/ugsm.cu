@@ -102,6 +102,7 @@ struct ugsm_handle {
     int k2s_min_seg = 24;     // shortest row segment of a strip (UGSM_K2S_MIN_SEG)
     long k2s_min_pixels = 400000;   // k2_stream runs levels of at least this many pixels (UGSM_K2S_MIN_PIXELS) ...
     int k2s_max_passes = 10;        // ... and at most this many smoothing passes (UGSM_K2S_MAX_PASSES)
+    int k2_tma = 1;                 // k2_stream's loader uses TMA tile loads (UGSM_K2_TMA)
     int pdl = 1;                    // programmatic dependent launch of the coarse-level kernels (UGSM_PDL)
     int k2s_edge_extra = 2;         // extra row segments of the edge strips, whose steps are slower (UGSM_K2S_EDGE_EXTRA)
     long k2_tiny_pixels = 20000;     // levels below this use k2_tiny_tile-sided k2_smooth_box_small tiles (UGSM_K2_TINY_PIXELS)
@@ -289,6 +290,7 @@ int set_kernel_attrs(ugsm_handle* h) {
     if (const char* e = getenv("UGSM_K2S_MIN_PIXELS")) h->k2s_min_pixels = atol(e);
     if (const char* e = getenv("UGSM_K2S_EDGE_EXTRA")) h->k2s_edge_extra = std::max(0, atoi(e));
     if (const char* e = getenv("UGSM_PDL")) h->pdl = atoi(e);
+    if (const char* e = getenv("UGSM_K2_TMA")) h->k2_tma = atoi(e);
     if (const char* e = getenv("UGSM_K2S_MAX_PASSES")) h->k2s_max_passes = std::min(K2S_MAX_PASSES, std::max(0, atoi(e)));
     CK(cudaFuncSetAttribute(k2_stream<K2S_NT_SMALL, K2S_MINB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)k2s_smem_bytes(K2S_NT_SMALL / 32 - 2)));
@@ -441,6 +443,12 @@ void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci
         nseg = std::min(nseg, std::max(1, brows / h->k2s_min_seg));
         sp.nseg = nseg;
         sp.edge_extra = h->k2s_edge_extra;
+        {   // input rows as TMA tiles: descriptors over pitch x hh floats (pad columns read as the cp.async loader does)
+            const float* src[3] = {Hi, Vi, Ci};
+            bool tma = h->k2_tma != 0;
+            for (int k = 0; k < 3 && tma; k++) tma = make_plane_map(h, &sp.tm[k], src[k], pitch, hh, pitch, K2_BW, 1);
+            sp.use_tma = tma ? 1 : 0;
+        }
         dim3 grid(strips, nseg + sp.edge_extra);
         if ((passes + 2) * 32 <= K2S_NT_SMALL)
             k2_stream<K2S_NT_SMALL, K2S_MINB_SMALL><<<grid, (passes + 2) * 32, k2s_smem_bytes(passes), h->stream>>>(sp);

@@ -6,7 +6,8 @@
 // sides (1.77x the useful work at S = 10) and pays one CTA-wide barrier per pass with nothing else resident.
 //
 // Here a CTA owns a 128-column strip and a row segment, and the passes form a producer/consumer pipeline down the
-// rows: warp 0 streams input rows into shared memory (cp.async, 16 bytes per lane, zero fill outside the image),
+// rows: warp 0 streams input rows into shared memory (2-D TMA tiles of 128 x 1 floats per plane completing on the
+// mbarrier of the row's ring slot, zero fill outside the allocation; cp.async where no tensor map can be built),
 // warp t (1..S) turns rows r-1, r, r+1 of pass t-1 into row r of pass t, and the last warp applies the 3x3 box
 // filter and stores.  A pass lags its producer by two rows and all stages advance together, one row per tick, with
 // one CTA barrier per tick (a variant coupled through full / empty mbarriers per ring row instead was measured
@@ -25,6 +26,7 @@
 // not set the kernel's time; row 0 and row H-1 take the GENERIC step, which reloads its three rows and applies
 // every border rule.
 #pragma once
+#include "ugsm_k1_stream.cuh"  // TMA / mbarrier helpers (k1s_mbar_*, k1s_tma_load_2d)
 #include "ugsm_kernels.cuh"
 
 namespace ugsm {
@@ -40,10 +42,14 @@ struct K2StreamParams {
     K2Params k;       // th is unused; hpad = column halo (multiple of 4, >= passes + 1)
     int nseg;         // row segments of an interior strip over [y_begin, y_end); edge strips use nseg + edge_extra
     int edge_extra;   // grid.y = nseg + edge_extra
+    int use_tma;      // the loader fetches rows as TMA tiles (tm[]) instead of cp.async
+    // TMA descriptors of the three input planes: pitch x h floats, box 128 x 1, zero fill outside (same cells as the
+    // cp.async loader's zero fill: columns outside the allocation, rows are never requested outside the image)
+    alignas(64) CUtensorMap tm[3];
 };
 
 __host__ __device__ inline size_t k2s_smem_bytes(int passes) {
-    return ((size_t)K2S_RING0F + (size_t)passes * K2S_RINGF) * sizeof(float);
+    return ((size_t)K2S_RING0F + (size_t)passes * K2S_RINGF) * sizeof(float) + K2S_D0 * sizeof(unsigned long long);
 }
 
 __device__ __forceinline__ void k2s_cp_async16(float* smem_dst, const float* gsrc, bool valid) {
@@ -138,7 +144,7 @@ __device__ __forceinline__ void k2s_fast_rows(const K2sRing& in, const K2sRing& 
 // NT = threads the launch may use ((passes + 2) * 32 <= NT); MINB = CTAs per SM the register budget is cut for.
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k2_stream(const __grid_constant__ K2StreamParams sp) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const K2Params& p = sp.k;
     const int S = p.passes, m = 1;  // m: rows / columns the 3x3 box filter reaches beyond the last pass
     const int W = p.w, Hh = p.h, pitch = p.pitch;
@@ -172,24 +178,56 @@ __global__ void __launch_bounds__(NT, MINB) k2_stream(const __grid_constant__ K2
     };
 
     if (warp == 0) {
-        // ---- loader: input rows -> ring 0, 16 bytes per lane per plane, zero fill outside the allocation ----
+        // ---- loader: input rows -> ring 0, zero fill outside the allocation ----
         const K2sRing out = ring(0);
-        const bool col_in = (gx0 >= 0 && gx0 + 3 < pitch);
-        auto issue = [&](int r) {
-            if (r >= out.lo && r <= out.hi) {
-                const size_t o = col_in ? (size_t)r * pitch + gx0 : 0;
-                float* d = out.own + out.slot(r);
-                k2s_cp_async16(d, p.Hi + o, col_in);
-                k2s_cp_async16(d + K2_BW, p.Vi + o, col_in);
-                k2s_cp_async16(d + 2 * K2_BW, p.Ci + o, col_in);
+        if (sp.use_tma) {
+            // a row of the three planes = three 2-D TMA tiles (128 x 1 floats each, 512-byte slots of the ring) that
+            // complete on the mbarrier of the row's ring slot; one elected lane issues, the whole warp waits
+            unsigned long long* bars = reinterpret_cast<unsigned long long*>(rings + K2S_RING0F + (size_t)S * K2S_RINGF);
+            if (lane == 0) {
+                for (int i = 0; i < K2S_D0; i++) k1s_mbar_init((unsigned)__cvta_generic_to_shared(&bars[i]), 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        for (int r = Rin0; r < Rin0 + K2S_LEAD; r++) issue(r);
-        for (int tau = 0; tau < T; tau++) {
-            issue(Rin0 + tau + K2S_LEAD);
-            asm volatile("cp.async.wait_group %0;" ::"n"(K2S_LEAD) : "memory");  // row Rin0 + tau has landed
-            __syncthreads();
+            __syncwarp();
+            auto issue = [&](int r) {
+                if (r >= out.lo && r <= out.hi && lane == 0) {
+                    const int sl = r & out.mask;
+                    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bars[sl]);
+                    float* d = rings + sl * K2S_SLOTF;
+                    // the slot's previous tenant was last read before the CTA barrier of the previous tick
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    k1s_mbar_expect_tx(bar, 3 * K2_BW * (int)sizeof(float));
+#pragma unroll
+                    for (int k = 0; k < 3; k++) k1s_tma_load_2d(d + k * K2_BW, &sp.tm[k], X0, r, bar);
+                }
+            };
+            for (int r = Rin0; r < Rin0 + K2S_LEAD; r++) issue(r);
+            for (int tau = 0; tau < T; tau++) {
+                issue(Rin0 + tau + K2S_LEAD);
+                const int r = Rin0 + tau;  // this row must have landed
+                if (r >= out.lo && r <= out.hi)
+                    k1s_mbar_wait((unsigned)__cvta_generic_to_shared(&bars[r & out.mask]), ((r - out.lo) >> 3) & 1);
+                __syncthreads();
+            }
+        } else {
+            // 16 bytes per lane per plane with cp.async (planes a tensor map cannot describe)
+            const bool col_in = (gx0 >= 0 && gx0 + 3 < pitch);
+            auto issue = [&](int r) {
+                if (r >= out.lo && r <= out.hi) {
+                    const size_t o = col_in ? (size_t)r * pitch + gx0 : 0;
+                    float* d = out.own + out.slot(r);
+                    k2s_cp_async16(d, p.Hi + o, col_in);
+                    k2s_cp_async16(d + K2_BW, p.Vi + o, col_in);
+                    k2s_cp_async16(d + 2 * K2_BW, p.Ci + o, col_in);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            for (int r = Rin0; r < Rin0 + K2S_LEAD; r++) issue(r);
+            for (int tau = 0; tau < T; tau++) {
+                issue(Rin0 + tau + K2S_LEAD);
+                asm volatile("cp.async.wait_group %0;" ::"n"(K2S_LEAD) : "memory");  // row Rin0 + tau has landed
+                __syncthreads();
+            }
         }
     } else if (warp <= S) {
         // ---- smoothing pass t = warp: rows r-1, r, r+1 of ring t-1 -> row r of ring t (ML:1106-1133) ----
