@@ -174,8 +174,8 @@ def test_match_level_bit_exact_vs_live_reference_cuda(gpu, tmp_path):
 
 @pytest.mark.parametrize("level,iters,passes", [(13, 2, 10), (11, 6, 5)])
 def test_large_kernels_bit_exact_vs_live_reference_cuda(capi, tmp_path, level, iters, passes):
-    """The LARGE-level kernels (k1_stream above 400 k pixels; the tiled k2_smooth_box at S = 10 and the pipelined
-    k2_stream at S = 5) against the UNMODIFIED reference CUDA code run live on the same GPU at 1024x768 (W % 128 = 0,
+    """The LARGE-level kernels (k1_stream with its TMA tile loads; the row-pipelined k2_stream at S = 10 and at
+    S = 5) against the UNMODIFIED reference CUDA code run live on the same GPU at 1024x768 (W % 128 = 0,
     H % 64 = 0: no out-of-bounds accidents in the reference, 786 k pixels: above both switch points): the finest-level
     schedule (reference level 13: 2 iterations, S = 10) and the third-finest (level 11: 6 iterations, S = 5, threshold
     schedule), bit-exact with no oracle in between, in the FAST and in the GENERIC march of K1."""
