@@ -193,3 +193,23 @@ def test_batch_driver_matches_a_tiff_list(capi, tmp_path):
     with capi.Handle() as h:
         want = h.match_full(*pairs[1])[0]
     assert rec["h_sum"] == pytest.approx(float(want.astype(np.float64).sum()), rel=1e-9, abs=1e-6)
+
+
+def test_feeder_odd_list_follows_the_reference_reader(capi, tmp_path):
+    """Settings::nextImage with an odd number of entries: after the last entry the index is reset to size - 2, so the
+    second pair of a 3-entry list is (entry 2, entry 1), then (2, 1) again."""
+    import shutil
+    names = ["rgb_none.tif", "rgb_lzw.tif", "rgb_packbits.tif"]
+    for n in names:
+        shutil.copy(os.path.join(HERE, n), tmp_path / n)
+    (tmp_path / "l.xml").write_text('<?xml version="1.0"?>\n<opencv_storage>\n<images>\n"%s"\n%s\n%s\n</images>\n'
+                                    "</opencv_storage>\n" % tuple(names))  # a quoted entry as FileStorage allows
+    with capi.Feeder(str(tmp_path / "l.xml"), pairs=3, slots=2, threads=2) as f:
+        assert f.info().list_images == 3
+        want = [(0, 1), (2, 1), (2, 1)]
+        for i, (a, b) in enumerate(want):
+            p, left, right = f.next()
+            assert p.index == i
+            assert np.array_equal(left, EXPECTED[names[a]]) and np.array_equal(right, EXPECTED[names[b]])
+            f.release(p.slot)
+        assert f.next() is None
