@@ -431,8 +431,8 @@ void launch_k2(ugsm_handle* h, const float* Hi, const float* Vi, const float* Ci
     }
     p.hpad = align_up(R, 4);
     if (h->k2_stream && passes <= h->k2s_max_passes && (long)w * hh >= h->k2s_min_pixels) {
-        // S <= 6 on levels of 1.5 MP and more: row pipeline over the passes (k2_stream), row segments sized for one
-        // co-resident wave.  (At S = 10 its 12-warp CTA is alone on an SM and the tiled kernel wins; measured.)
+        // levels of 400 k pixels and more, S <= 10: row pipeline over the passes (k2_stream), row segments sized for
+        // one co-resident wave (two CTAs per SM)
         K2StreamParams sp;
         sp.k = p;
         sp.k.th = 0;
