@@ -144,12 +144,12 @@ __device__ __forceinline__ void k2s_fast_rows(const K2sRing& in, const K2sRing& 
 // NT = threads the launch may use ((passes + 2) * 32 <= NT); MINB = CTAs per SM the register budget is cut for.
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k2_stream(const __grid_constant__ K2StreamParams sp) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char k2s_smem[];
     const K2Params& p = sp.k;
     const int S = p.passes, m = 1;  // m: rows / columns the 3x3 box filter reaches beyond the last pass
     const int W = p.w, Hh = p.h, pitch = p.pitch;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* const rings = reinterpret_cast<float*>(smem_raw);  // ring 0: [8][3][128]; rings 1..S: [4][3][128]
+    float* const rings = reinterpret_cast<float*>(k2s_smem);  // ring 0: [8][3][128]; rings 1..S: [4][3][128]
     const int TWu = K2_BW - 2 * p.hpad;        // useful columns per strip
     const int X0 = blockIdx.x * TWu - p.hpad;  // image column of strip column 0
     // strips whose 128 columns all have both neighbours inside the image need no column rule at all
