@@ -159,58 +159,72 @@ int parse_tiff(const uint8_t* buf, size_t n, TiffInfo& t) {
     return UGSM_OK;
 }
 
-// TIFF LZW (MSB-first codes, 9..12 bits, "early change").  Returns the number of bytes written.
+// TIFF LZW (MSB-first codes, 9..12 bits, "early change").  Returns the number of bytes written.  Strings are emitted
+// back to back, so the string of a table entry -- the previous string plus the first byte of the current one -- is a
+// contiguous run of the OUTPUT: an entry is (position, length) and decoding a code is a forward copy of earlier
+// output in 8-byte pieces (the bytes a piece copies beyond the string's end are overwritten by the next string).  The
+// 256 literals are a table in front of the output (K_LZW_PREFIX bytes, which the caller provides before `dst`, plus
+// 16 bytes of slack behind `cap`), so literal and string codes take the same path: no data-dependent branch per code.
+constexpr size_t K_LZW_PREFIX = 272;  // 256 literals + 8 bytes an 8-byte piece may read past the last one, 16-aligned
 size_t lzw_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
-    struct Ent { uint16_t prev; uint16_t len; uint8_t first, last; };
-    static thread_local std::vector<Ent> tab(4096 + 2);
-    for (int i = 0; i < 256; i++) tab[i] = Ent{0xffff, 1, (uint8_t)i, (uint8_t)i};
+    struct Ent { uint32_t pos, len; };  // string = base[pos .. pos + len), base = dst - K_LZW_PREFIX
+    static thread_local Ent tab[4096 + 2];
+    uint8_t* const base = dst - K_LZW_PREFIX;
+    for (uint32_t i = 0; i < 256; i++) base[i] = (uint8_t)i, tab[i] = Ent{i, 1};
     uint32_t next = 258, bits = 9;
-    uint64_t acc = 0;
+    uint64_t acc = 0;  // valid bits at the top
     int nacc = 0;
-    size_t ip = 0, op = 0;
-    int prev = -1;
+    size_t ip = 0;
+    uint32_t op = (uint32_t)K_LZW_PREFIX;
+    const uint32_t end = (uint32_t)(K_LZW_PREFIX + cap);
+    uint32_t ppos = 0, plen = 0;  // the previous string
+    bool have_prev = false;
     for (;;) {
-        while (nacc < (int)bits && ip < n) acc = acc << 8 | src[ip++], nacc += 8;
+        if (nacc <= 32) {
+            if (ip + 4 <= n) {
+                const uint32_t w = (uint32_t)src[ip] << 24 | (uint32_t)src[ip + 1] << 16 | (uint32_t)src[ip + 2] << 8 | src[ip + 3];
+                acc |= (uint64_t)w << (32 - nacc);
+                ip += 4, nacc += 32;
+            } else {
+                while (nacc <= 56 && ip < n) acc |= (uint64_t)src[ip++] << (56 - nacc), nacc += 8;
+            }
+        }
         if (nacc < (int)bits) break;
-        const uint32_t code = (uint32_t)(acc >> (nacc - bits)) & ((1u << bits) - 1);
-        nacc -= bits;
-        if (code == 257) break;
+        const uint32_t code = (uint32_t)(acc >> (64 - bits));
+        acc <<= bits;
+        nacc -= (int)bits;
         if (code == 256) {
-            next = 258, bits = 9, prev = -1;
+            next = 258, bits = 9, have_prev = false;
             continue;
         }
-        if (prev < 0) {
-            if (code > 255 || op >= cap) break;
-            dst[op++] = (uint8_t)code;
-            prev = (int)code;
-            continue;
+        if (code == 257 || op >= end) break;
+        if (code > next || (code == next && !have_prev) || (code >= 258 && !have_prev)) break;  // corrupt stream
+        uint32_t slen;
+        if (code < 256) {  // literal: the common case on noisy images, kept off the table path
+            base[op] = (uint8_t)code;
+            slen = 1;
+        } else {
+            const bool kwkwk = (code == next);
+            const uint32_t spos = kwkwk ? ppos : tab[code].pos;
+            const uint32_t cl = kwkwk ? plen : tab[code].len;  // bytes copied from earlier output
+            slen = cl + (kwkwk ? 1u : 0u);
+            if (op + slen > end) {  // the last strip may carry padding: copy what fits
+                for (uint32_t i = 0; op + i < end; i++) base[op + i] = (kwkwk && i == cl) ? base[ppos] : base[spos + i];
+                op = end;
+                break;
+            }
+            for (uint32_t i = 0; i < cl; i += 8) memcpy(base + op + i, base + spos + i, 8);
+            if (kwkwk) base[op + cl] = base[ppos];
         }
-        uint32_t cur = code;
-        if (code > next || next >= 4096 + 1) break;  // corrupt stream
-        const bool kwkwk = (code == next);
-        if (kwkwk) cur = (uint32_t)prev;
-        const uint32_t len = tab[cur].len + (kwkwk ? 1 : 0);
-        if (op + len > cap) {  // the last strip may carry padding: copy what fits
-            std::vector<uint8_t> tmp(len);
-            size_t q = len;
-            if (kwkwk) tmp[--q] = tab[cur].first;
-            for (uint32_t c = cur; q > 0; c = tab[c].prev) tmp[--q] = tab[c].last;
-            memcpy(dst + op, tmp.data(), cap - op);
-            op = cap;
-            break;
-        }
-        size_t q = op + len;
-        if (kwkwk) dst[--q] = tab[cur].first;
-        for (uint32_t c = cur; q > op; c = tab[c].prev) dst[--q] = tab[c].last;
-        op += len;
-        if (next < 4096) {
-            tab[next] = Ent{(uint16_t)prev, (uint16_t)(tab[prev].len + 1), tab[prev].first, kwkwk ? tab[prev].first : tab[code].first};
+        if (have_prev && next < 4096) {
+            tab[next] = Ent{ppos, plen + 1};
             next++;
             if (next + 1 >= (1u << bits) && bits < 12) bits++;  // early change: switch one code early
         }
-        prev = (int)code;
+        ppos = op, plen = slen, have_prev = true;
+        op += slen;
     }
-    return op;
+    return op - K_LZW_PREFIX;
 }
 
 size_t packbits_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
@@ -382,8 +396,8 @@ int decode_tiff(const uint8_t* buf, size_t n, const TiffInfo& t, uint8_t* dst, s
             const size_t x0 = cx * cw, cols_img = (x0 + cw <= t.width) ? cw : t.width - x0;
             const size_t np = t.planar == 2 ? used : 1;
             for (size_t s = 0; s < np; s++) {
-                raw[s].resize(rows_dec * cw * csamples * bpsb);
-                const int rc = decode_chunk(r, t, s * per_plane + cy * across + cx, raw[s].data(), rows_dec, cw * csamples);
+                raw[s].resize(K_LZW_PREFIX + rows_dec * cw * csamples * bpsb + 16);  // literal table in front, slack behind
+                const int rc = decode_chunk(r, t, s * per_plane + cy * across + cx, raw[s].data() + K_LZW_PREFIX, rows_dec, cw * csamples);
                 if (rc != UGSM_OK) return rc;
             }
             for (size_t y = 0; y < rows_img; y++) {
@@ -391,12 +405,12 @@ int decode_tiff(const uint8_t* buf, size_t n, const TiffInfo& t, uint8_t* dst, s
                 const size_t row_off = y * cw * csamples * bpsb;
                 if (t.planar == 2) {
                     for (size_t s = 0; s < used; s++) {
-                        finish_row(t, raw[s].data() + row_off, cw, 1);
-                        planes[s] = raw[s].data() + row_off;
+                        finish_row(t, raw[s].data() + K_LZW_PREFIX + row_off, cw, 1);
+                        planes[s] = raw[s].data() + K_LZW_PREFIX + row_off;
                     }
                 } else {
-                    finish_row(t, raw[0].data() + row_off, cw, t.spp);
-                    for (size_t s = 0; s < used; s++) planes[s] = raw[0].data() + row_off + s * bpsb;
+                    finish_row(t, raw[0].data() + K_LZW_PREFIX + row_off, cw, t.spp);
+                    for (size_t s = 0; s < used; s++) planes[s] = raw[0].data() + K_LZW_PREFIX + row_off + s * bpsb;
                 }
                 emit_bgr(t, planes, csamples, cols_img, dst + (y0 + y) * step + 3 * x0);
             }
