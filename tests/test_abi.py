@@ -103,7 +103,8 @@ def test_header_is_plain_c(tmp_path):
     src.write_text('#include <stdio.h>\n#include "ugsm.h"\n'
                    'int main(void) { ugsm_config c; ugsm_dims d; ugsm_config_default(&c);\n'
                    '  if (ugsm_query_dims(&c, 3264, 4928, 1, &d) != UGSM_OK) return 2;\n'
-                   '  printf("%d %d %d %s\\n", c.levels, d.fov_width, d.fov_height, ugsm_version()); return 0; }\n')
+                   '  printf("%d %d %d %s %d %d\\n", c.levels, d.fov_width, d.fov_height, ugsm_version(),\n'
+                   '         (int)sizeof(ugsm_feeder_pair), (int)sizeof(ugsm_feeder_info_t)); return 0; }\n')
     exe = str(tmp_path / "use")
     lib_dir = os.path.join(root, "ug_stereomatcher_b200")
     p = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
@@ -112,3 +113,5 @@ def test_header_is_plain_c(tmp_path):
     assert p.returncode == 0, p.stderr.decode()
     out = subprocess.run([exe], stdout=subprocess.PIPE).stdout.decode().split()
     assert out[:3] == ["14", "615", "407"]
+    from ug_stereomatcher_b200 import capi
+    assert [int(out[-2]), int(out[-1])] == [C.sizeof(capi.FeederPair), C.sizeof(capi.FeederInfo)]  # ctypes mirrors
